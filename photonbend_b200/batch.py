@@ -1,0 +1,102 @@
+"""Frame streams: many frames that share one geometry (a video, BASELINE config 5).
+
+The reference has no such entry point -- its commands remap one image per process.  Two things
+make a stream cheap on a B200:
+
+* the source index of an output pixel depends on the geometry only, so one launch resolves it
+  once and applies it to every frame of a device batch (``pb_remap_u8`` with n_frames > 1);
+* host <-> device copies of neighbouring frames overlap with each other and with the kernel
+  when they are issued on separate CUDA streams from pinned memory (``FramePipeline``).
+
+Sharding over the GPUs of a box needs no collective: frame k goes to GPU k mod G
+(``shard_frames``), every GPU owns its inputs and outputs.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+from photonbend_b200 import engine
+from photonbend_b200.core.coordinate_map import CoordinateMap
+
+
+def shard_frames(n_frames: int, rank: int, world_size: int) -> range:
+    """Indices of the frames rank ``rank`` of ``world_size`` processes: k = rank (mod world_size).
+    Round-robin keeps every GPU's share within one frame of the others for any stream length."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of size {world_size}")
+    return range(rank, n_frames, world_size)
+
+
+def remap_batch(source, coordinate_map: CoordinateMap, frames, out=None):
+    """Remap a device batch ``frames`` (uint8 CUDA tensor (N, H, W, C)) that shares the geometry
+    of ``source`` (a CameraImage / DoubleCameraImage / PanoramaImage whose own ``image`` is only
+    used for its shape) along ``coordinate_map``.  One kernel launch; returns the (N, Ho, Wo, C)
+    CUDA tensor."""
+    if not (isinstance(coordinate_map, CoordinateMap) and coordinate_map.is_lazy):
+        raise ValueError("remap_batch needs the lazy CoordinateMap of get_coordinate_map()")
+    if frames.dim() != 4 or not frames.is_cuda:
+        raise ValueError("frames must be a CUDA tensor of shape (N, H, W, C)")
+    return engine.remap_device(coordinate_map.rays, source._source_geometry(), frames.contiguous(), out)
+
+
+class FramePipeline:
+    """Host frames in, host frames out, with ``depth`` frames in flight.
+
+    Slot s owns a device input buffer, a device output buffer and a CUDA stream; frame k uses
+    slot k mod depth: H2D copy, fused remap kernel and D2H copy are enqueued on that stream, so
+    the copies of frame k+1 overlap the kernel and the D2H of frame k.  Host buffers should be
+    pinned (``torch.empty(..., pin_memory=True)``) or the copies serialise.
+    """
+
+    def __init__(self, source, coordinate_map: CoordinateMap, depth: int = 3, device: Optional[int] = None):
+        if not (isinstance(coordinate_map, CoordinateMap) and coordinate_map.is_lazy):
+            raise ValueError("FramePipeline needs the lazy CoordinateMap of get_coordinate_map()")
+        torch = engine._torch()
+        self._torch = torch
+        self._rays = coordinate_map.rays
+        self._src_geom = source._source_geometry()
+        self._device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self._depth = max(1, int(depth))
+        self._streams = [torch.cuda.Stream(device=self._device) for _ in range(self._depth)]
+        self._src_bufs: List = [None] * self._depth
+        self._dst_bufs: List = [None] * self._depth
+        self._submitted = 0
+        self.kernel_launches = 0
+
+    @property
+    def output_shape(self):
+        return (self._rays.out.height, self._rays.out.output_width)
+
+    def submit(self, host_frame, host_out):
+        """Enqueue one frame: host_frame (uint8 CPU tensor (H, W, C)) -> host_out (uint8 CPU
+        tensor (Ho, Wo, C)).  Returns immediately; ``host_out`` is complete after ``drain()``
+        (or after the returned event)."""
+        torch = self._torch
+        slot = self._submitted % self._depth
+        self._submitted += 1
+        stream = self._streams[slot]
+        with torch.cuda.device(self._device), torch.cuda.stream(stream):
+            if self._src_bufs[slot] is None or self._src_bufs[slot].shape != host_frame.shape:
+                self._src_bufs[slot] = torch.empty(host_frame.shape, dtype=torch.uint8, device=self._device)
+                self._dst_bufs[slot] = None
+            src_dev = self._src_bufs[slot]
+            src_dev.copy_(host_frame, non_blocking=True)
+            self._dst_bufs[slot] = engine.remap_device(self._rays, self._src_geom, src_dev, self._dst_bufs[slot])
+            self.kernel_launches += 1
+            host_out.copy_(self._dst_bufs[slot], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(stream)
+        return done
+
+    def run(self, host_frames: Sequence, host_outs: Sequence) -> None:
+        """Remap every frame of ``host_frames`` into the matching ``host_outs`` and wait."""
+        if len(host_frames) != len(host_outs):
+            raise ValueError("host_frames and host_outs differ in length")
+        for frame, out in zip(host_frames, host_outs):
+            self.submit(frame, out)
+        self.drain()
+
+    def drain(self) -> None:
+        for s in self._streams:
+            s.synchronize()

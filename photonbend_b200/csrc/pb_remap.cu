@@ -1,0 +1,407 @@
+// pb_remap.cu -- kernels and C ABI of libpbremap.so (see include/pb_remap.h).
+//
+// Build (photonbend_b200/build.py):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//        -Xcompiler -fPIC,-ffp-contract=off -shared -Iinclude -o libpbremap.so pb_remap.cu
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "pb_device.cuh"
+
+namespace pb {
+
+// ------------------------------------------------------------------------------------ errors
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(PB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// ------------------------------------------------------------------------------------ host-side derivation
+// Everything below is evaluated in the reference's order of operations; this translation unit's
+// host code is compiled with -ffp-contract=off so no product is fused into a sum.
+
+static double to_radians(double deg) { return deg / 180 * kPi; }  // utils/__init__.py:27-37
+
+static double linspace_step(double start, double stop, int n) {
+    return n > 1 ? (stop - start) / (double)(n - 1) : 0.0;
+}
+
+static int check_image(const pb_image_desc& d, const char* which) {
+    if (d.kind < PB_KIND_CAMERA || d.kind > PB_KIND_EQUIRECT)
+        return fail(PB_ERR_INVALID_ARGUMENT, std::string(which) + ": unknown image kind");
+    if (d.height < 1 || d.width < 1)
+        return fail(PB_ERR_INVALID_ARGUMENT, std::string(which) + ": height and width must be positive");
+    if ((long long)d.height * (long long)d.width >= (1LL << 31))
+        return fail(PB_ERR_UNSUPPORTED, std::string(which) + ": more than 2^31 pixels");
+    if (d.kind != PB_KIND_EQUIRECT && (d.lens < PB_LENS_EQUIDISTANT || d.lens > PB_LENS_THOBY))
+        return fail(PB_ERR_INVALID_ARGUMENT, std::string(which) + ": unknown lens");
+    if (d.kind == PB_KIND_DOUBLE && d.width < 2)
+        return fail(PB_ERR_INVALID_ARGUMENT, std::string(which) + ": a double image needs width >= 2");
+    return PB_OK;
+}
+
+static OutGeom derive_out(const pb_image_desc& d) {
+    OutGeom g;
+    std::memset(&g, 0, sizeof(g));
+    g.kind = d.kind;
+    g.lens = d.lens;
+    g.H = d.height;
+    g.W = d.width;
+    g.f = d.f_distance;
+    const double h = (double)d.height;
+    if (d.kind == PB_KIND_EQUIRECT) {
+        // projection.py:499-505
+        const double w = (double)d.width;
+        const double half_px = kPi / w / 2;
+        g.x_start = -kPi + half_px;
+        g.x_stop = kPi - half_px;
+        g.x_step = linspace_step(g.x_start, g.x_stop, d.width);
+        g.y_start = 0.0;
+        g.y_stop = kPi;
+        g.y_step = linspace_step(g.y_start, g.y_stop, d.height);
+    } else {
+        int cols = d.width;
+        if (d.kind == PB_KIND_DOUBLE) {
+            // projection.py:355-360, 389-401
+            g.half_w = d.width / 2;
+            g.W = 2 * g.half_w;
+            cols = g.half_w;
+            g.right_lat_min = kPi - (d.fov / 2.0);
+        }
+        const double w = (double)cols;
+        g.half_fov = d.fov / 2;
+        g.x_start = -w / 2 + 0.5;  // projection.py:177
+        g.x_stop = w / 2 - 0.5;
+        g.x_step = linspace_step(g.x_start, g.x_stop, cols);
+        g.y_start = h / 2 - 0.5;   // projection.py:178-180
+        g.y_stop = -h / 2 + 0.5;
+        g.y_step = linspace_step(g.y_start, g.y_stop, d.height);
+    }
+    return g;
+}
+
+static SrcGeom derive_src(const pb_image_desc& d, int channels) {
+    SrcGeom s;
+    std::memset(&s, 0, sizeof(s));
+    s.kind = d.kind;
+    s.lens = d.lens;
+    s.H = d.height;
+    s.W = d.width;
+    s.C = channels;
+    s.f = d.f_distance;
+    s.rect_limit = to_radians(89);
+    const double h = (double)d.height, w = (double)d.width;
+    s.cy = h / 2 - 0.5;  // projection.py:274
+    s.cx = w / 2 - 0.5;
+    if (d.kind == PB_KIND_EQUIRECT) {
+        s.seg_w = kPi / (w / 2);  // projection.py:539-543
+        s.seg_h = kPi / h;
+        s.half_w = w / 2;
+    } else if (d.kind == PB_KIND_DOUBLE) {
+        s.wl = d.width / 2;       // projection.py:413
+        s.wr = d.width - s.wl;
+        s.cxl = (double)s.wl / 2 - 0.5;
+        s.cxr = (double)s.wr / 2 - 0.5;
+        const double ref = (d.fov / 2) - (kPi / 2);  // projection.py:414-418
+        s.mrg_lo = kPi / 2 - ref;
+        s.mrg_hi = kPi / 2 + ref;
+        s.mrg_span = 2.0 * ref;
+        s.mrg_hi_safe = s.mrg_hi + to_radians(0.5);
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------ kernels
+
+struct RemapArgs {
+    OutGeom out;
+    SrcGeom src;
+    Rotations rot;
+    const unsigned char* src_px;
+    unsigned char* dst_px;
+    long long src_frame_stride, dst_frame_stride;
+    int n_frames;
+};
+
+template <int C>
+__device__ __forceinline__ void copy_px(unsigned char* __restrict__ d, const unsigned char* __restrict__ s) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) d[c] = __ldg(s + c);
+}
+
+template <int C>
+__device__ __forceinline__ void zero_px(unsigned char* __restrict__ d) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) d[c] = 0;
+}
+
+// Generic fused remap: one thread resolves one output pixel (float64, every polar round trip
+// of the reference kept), then applies the resolved lookup to every frame of the batch.
+template <int OUT_KIND, int SRC_KIND, int C>
+__global__ void __launch_bounds__(256) remap_generic_kernel(const __grid_constant__ RemapArgs a) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= a.out.H || j >= a.out.W) return;
+
+    Ray r = output_ray<OUT_KIND>(a.out, i, j);
+    for (int k = 0; k < a.rot.n; ++k) r = rotate_ray(r, a.rot.m[k]);
+    const Lookup L = source_lookup<SRC_KIND>(a.src, r);
+
+    const long long dst_off = ((long long)i * a.out.W + j) * C;
+    for (int f = 0; f < a.n_frames; ++f) {
+        const unsigned char* __restrict__ sp = a.src_px + f * a.src_frame_stride;
+        unsigned char* __restrict__ dp = a.dst_px + f * a.dst_frame_stride + dst_off;
+        if (SRC_KIND != PB_KIND_DOUBLE) {
+            if (L.off0 >= 0) copy_px<C>(dp, sp + (long long)L.off0 * C);
+            else zero_px<C>(dp);
+        } else {
+            if (r.invalid) {
+                zero_px<C>(dp);
+                continue;
+            }
+            const unsigned char* p0 = sp + (long long)(L.off0 >= 0 ? L.off0 : 0) * C;
+            const unsigned char* p1 = sp + (long long)(L.off1 >= 0 ? L.off1 : 0) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const unsigned v0 = L.off0 >= 0 ? __ldg(p0 + c) : 0u;
+                const unsigned v1 = L.off1 >= 0 ? __ldg(p1 + c) : 0u;
+                dp[c] = blend_u8(v0, L.w0, v1, L.w1);
+            }
+        }
+    }
+}
+
+// get_coordinate_map() + n rotations, materialised.
+template <int OUT_KIND>
+__global__ void __launch_bounds__(256) materialize_map_kernel(const __grid_constant__ OutGeom out,
+                                                              const __grid_constant__ Rotations rot,
+                                                              double* __restrict__ map) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= out.H || j >= out.W) return;
+    Ray r = output_ray<OUT_KIND>(out, i, j);
+    for (int k = 0; k < rot.n; ++k) r = rotate_ray(r, rot.m[k]);
+    double* m = map + ((long long)i * out.W + j) * 3;
+    m[0] = r.lat;
+    m[1] = r.lon;
+    m[2] = r.invalid ? 1.0 : 0.0;
+}
+
+struct Mat3 {
+    double m[9];
+};
+
+__global__ void __launch_bounds__(256) rotate_map_kernel(const __grid_constant__ Mat3 mat, double* __restrict__ in,
+                                                         double* __restrict__ out, long long n) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    Ray r;
+    r.lat = in[p * 3 + 0];
+    r.lon = in[p * 3 + 1];
+    r.invalid = in[p * 3 + 2] != 0.0;
+    if (r.invalid) {  // rotation.py:124-125 zeroes the caller's map
+        in[p * 3 + 0] = 0.0;
+        in[p * 3 + 1] = 0.0;
+    }
+    r = rotate_ray(r, mat.m);
+    out[p * 3 + 0] = r.lat;
+    out[p * 3 + 1] = r.lon;
+    out[p * 3 + 2] = r.invalid ? 1.0 : 0.0;
+}
+
+template <int SRC_KIND, int C>
+__global__ void __launch_bounds__(256) gather_from_map_kernel(const __grid_constant__ SrcGeom src,
+                                                              double* __restrict__ map, long long n,
+                                                              const unsigned char* __restrict__ sp,
+                                                              unsigned char* __restrict__ dst) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    Ray r;
+    r.lat = map[p * 3 + 0];
+    r.lon = map[p * 3 + 1];
+    r.invalid = map[p * 3 + 2] != 0.0;
+    if (SRC_KIND == PB_KIND_EQUIRECT && r.invalid) {  // projection.py:533-536
+        map[p * 3 + 0] = 0.0;
+        map[p * 3 + 1] = 0.0;
+    }
+    const Lookup L = source_lookup<SRC_KIND>(src, r);
+    unsigned char* dp = dst + p * C;
+    if (SRC_KIND != PB_KIND_DOUBLE) {
+        if (L.off0 >= 0) copy_px<C>(dp, sp + (long long)L.off0 * C);
+        else zero_px<C>(dp);
+    } else {
+        if (r.invalid) {
+            zero_px<C>(dp);
+            return;
+        }
+        const unsigned char* p0 = sp + (long long)(L.off0 >= 0 ? L.off0 : 0) * C;
+        const unsigned char* p1 = sp + (long long)(L.off1 >= 0 ? L.off1 : 0) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const unsigned v0 = L.off0 >= 0 ? __ldg(p0 + c) : 0u;
+            const unsigned v1 = L.off1 >= 0 ? __ldg(p1 + c) : 0u;
+            dp[c] = blend_u8(v0, L.w0, v1, L.w1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ launchers
+
+template <int OUT_KIND, int SRC_KIND>
+static void launch_generic_c(const RemapArgs& a, cudaStream_t st) {
+    dim3 block(32, 8);
+    dim3 grid((a.out.W + block.x - 1) / block.x, (a.out.H + block.y - 1) / block.y);
+    switch (a.src.C) {
+        case 1: remap_generic_kernel<OUT_KIND, SRC_KIND, 1><<<grid, block, 0, st>>>(a); break;
+        case 2: remap_generic_kernel<OUT_KIND, SRC_KIND, 2><<<grid, block, 0, st>>>(a); break;
+        case 3: remap_generic_kernel<OUT_KIND, SRC_KIND, 3><<<grid, block, 0, st>>>(a); break;
+        default: remap_generic_kernel<OUT_KIND, SRC_KIND, 4><<<grid, block, 0, st>>>(a); break;
+    }
+}
+
+template <int OUT_KIND>
+static void launch_generic_s(const RemapArgs& a, cudaStream_t st) {
+    switch (a.src.kind) {
+        case PB_KIND_CAMERA: launch_generic_c<OUT_KIND, PB_KIND_CAMERA>(a, st); break;
+        case PB_KIND_DOUBLE: launch_generic_c<OUT_KIND, PB_KIND_DOUBLE>(a, st); break;
+        default: launch_generic_c<OUT_KIND, PB_KIND_EQUIRECT>(a, st); break;
+    }
+}
+
+static void launch_generic(const RemapArgs& a, cudaStream_t st) {
+    switch (a.out.kind) {
+        case PB_KIND_CAMERA: launch_generic_s<PB_KIND_CAMERA>(a, st); break;
+        case PB_KIND_DOUBLE: launch_generic_s<PB_KIND_DOUBLE>(a, st); break;
+        default: launch_generic_s<PB_KIND_EQUIRECT>(a, st); break;
+    }
+}
+
+template <int SRC_KIND>
+static void launch_gather_c(const SrcGeom& s, double* map, long long n, const unsigned char* sp,
+                            unsigned char* dst, cudaStream_t st) {
+    const int block = 256;
+    const unsigned grid = (unsigned)((n + block - 1) / block);
+    switch (s.C) {
+        case 1: gather_from_map_kernel<SRC_KIND, 1><<<grid, block, 0, st>>>(s, map, n, sp, dst); break;
+        case 2: gather_from_map_kernel<SRC_KIND, 2><<<grid, block, 0, st>>>(s, map, n, sp, dst); break;
+        case 3: gather_from_map_kernel<SRC_KIND, 3><<<grid, block, 0, st>>>(s, map, n, sp, dst); break;
+        default: gather_from_map_kernel<SRC_KIND, 4><<<grid, block, 0, st>>>(s, map, n, sp, dst); break;
+    }
+}
+
+}  // namespace pb
+
+// ------------------------------------------------------------------------------------ C ABI
+
+using namespace pb;
+
+extern "C" {
+
+int pb_version(void) { return PB_ABI_VERSION; }
+
+const char* pb_last_error(void) { return g_last_error.c_str(); }
+
+int32_t pb_output_width(const pb_image_desc* out) {
+    if (!out) return 0;
+    return out->kind == PB_KIND_DOUBLE ? 2 * (out->width / 2) : out->width;
+}
+
+int pb_remap_u8(const pb_remap_desc* desc, const uint8_t* src, int64_t src_frame_stride, uint8_t* dst,
+                int64_t dst_frame_stride, int32_t n_frames, void* stream) {
+    if (!desc || !src || !dst) return fail(PB_ERR_INVALID_ARGUMENT, "pb_remap_u8: null pointer");
+    if (int rc = check_image(desc->out, "out")) return rc;
+    if (int rc = check_image(desc->src, "src")) return rc;
+    if (desc->channels < 1 || desc->channels > 4)
+        return fail(PB_ERR_UNSUPPORTED, "pb_remap_u8: channels must be 1..4");
+    if (desc->n_rotations < 0) return fail(PB_ERR_INVALID_ARGUMENT, "pb_remap_u8: negative n_rotations");
+    if (desc->n_rotations > PB_MAX_ROTATIONS)
+        return fail(PB_ERR_TOO_MANY_ROTATIONS, "pb_remap_u8: more than PB_MAX_ROTATIONS rotations");
+    if (n_frames < 0) return fail(PB_ERR_INVALID_ARGUMENT, "pb_remap_u8: negative n_frames");
+    if (n_frames == 0) return PB_OK;
+
+    RemapArgs a;
+    a.out = derive_out(desc->out);
+    a.src = derive_src(desc->src, desc->channels);
+    a.rot.n = desc->n_rotations;
+    std::memcpy(a.rot.m, desc->rotations, sizeof(a.rot.m));
+    a.src_px = src;
+    a.dst_px = dst;
+    a.src_frame_stride = src_frame_stride;
+    a.dst_frame_stride = dst_frame_stride;
+    a.n_frames = n_frames;
+    launch_generic(a, (cudaStream_t)stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "pb_remap_u8 launch");
+    return PB_OK;
+}
+
+int pb_materialize_map_f64(const pb_remap_desc* desc, double* map, void* stream) {
+    if (!desc || !map) return fail(PB_ERR_INVALID_ARGUMENT, "pb_materialize_map_f64: null pointer");
+    if (int rc = check_image(desc->out, "out")) return rc;
+    if (desc->n_rotations < 0) return fail(PB_ERR_INVALID_ARGUMENT, "pb_materialize_map_f64: negative n_rotations");
+    if (desc->n_rotations > PB_MAX_ROTATIONS)
+        return fail(PB_ERR_TOO_MANY_ROTATIONS, "pb_materialize_map_f64: more than PB_MAX_ROTATIONS rotations");
+    OutGeom g = derive_out(desc->out);
+    Rotations rot;
+    rot.n = desc->n_rotations;
+    std::memcpy(rot.m, desc->rotations, sizeof(rot.m));
+    dim3 block(32, 8);
+    dim3 grid((g.W + block.x - 1) / block.x, (g.H + block.y - 1) / block.y);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (g.kind) {
+        case PB_KIND_CAMERA: materialize_map_kernel<PB_KIND_CAMERA><<<grid, block, 0, st>>>(g, rot, map); break;
+        case PB_KIND_DOUBLE: materialize_map_kernel<PB_KIND_DOUBLE><<<grid, block, 0, st>>>(g, rot, map); break;
+        default: materialize_map_kernel<PB_KIND_EQUIRECT><<<grid, block, 0, st>>>(g, rot, map); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "pb_materialize_map_f64 launch");
+    return PB_OK;
+}
+
+int pb_rotate_map_f64(const double matrix[9], double* map_in, double* map_out, int64_t n_pixels, void* stream) {
+    if (!matrix || !map_in || !map_out) return fail(PB_ERR_INVALID_ARGUMENT, "pb_rotate_map_f64: null pointer");
+    if (n_pixels < 0) return fail(PB_ERR_INVALID_ARGUMENT, "pb_rotate_map_f64: negative n_pixels");
+    if (map_in == map_out) return fail(PB_ERR_INVALID_ARGUMENT, "pb_rotate_map_f64: map_in and map_out alias");
+    if (n_pixels == 0) return PB_OK;
+    Mat3 m;
+    std::memcpy(m.m, matrix, sizeof(m.m));
+    const int block = 256;
+    const long long blocks = (n_pixels + block - 1) / block;
+    if (blocks > 0x7fffffffLL) return fail(PB_ERR_UNSUPPORTED, "pb_rotate_map_f64: map too large");
+    rotate_map_kernel<<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>(m, map_in, map_out, n_pixels);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "pb_rotate_map_f64 launch");
+    return PB_OK;
+}
+
+int pb_gather_from_map_u8(const pb_image_desc* src_desc, int32_t channels, double* map, int32_t map_height,
+                          int32_t map_width, const uint8_t* src, uint8_t* dst, void* stream) {
+    if (!src_desc || !map || !src || !dst) return fail(PB_ERR_INVALID_ARGUMENT, "pb_gather_from_map_u8: null pointer");
+    if (int rc = check_image(*src_desc, "src")) return rc;
+    if (channels < 1 || channels > 4) return fail(PB_ERR_UNSUPPORTED, "pb_gather_from_map_u8: channels must be 1..4");
+    if (map_height < 0 || map_width < 0) return fail(PB_ERR_INVALID_ARGUMENT, "pb_gather_from_map_u8: negative map size");
+    const long long n = (long long)map_height * map_width;
+    if (n == 0) return PB_OK;
+    if ((n + 255) / 256 > 0x7fffffffLL) return fail(PB_ERR_UNSUPPORTED, "pb_gather_from_map_u8: map too large");
+    SrcGeom s = derive_src(*src_desc, channels);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (s.kind) {
+        case PB_KIND_CAMERA: launch_gather_c<PB_KIND_CAMERA>(s, map, n, src, dst, st); break;
+        case PB_KIND_DOUBLE: launch_gather_c<PB_KIND_DOUBLE>(s, map, n, src, dst, st); break;
+        default: launch_gather_c<PB_KIND_EQUIRECT>(s, map, n, src, dst, st); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "pb_gather_from_map_u8 launch");
+    return PB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+"""Host-side engine: geometry descriptors, device buffers (torch is the plumbing for device
+memory and streams only) and the calls into libpbremap.so.
+
+Nothing here computes pixels on the CPU; a missing CUDA device or library is an error.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native
+
+_KIND_NAMES = {"camera": _native.KIND_CAMERA, "double": _native.KIND_DOUBLE,
+               "equirect": _native.KIND_EQUIRECT}
+
+
+@dataclass(frozen=True)
+class ImageGeometry:
+    """One side of a remap, as libpbremap.so wants it (pb_image_desc)."""
+
+    kind: int
+    height: int
+    width: int
+    lens: int = 0
+    fov: float = 0.0
+    f_distance: float = 0.0
+
+    @property
+    def output_width(self) -> int:
+        # a double image only has 2*(width//2) columns (reference projection.py:389-397)
+        return 2 * (self.width // 2) if self.kind == _native.KIND_DOUBLE else self.width
+
+    def fill(self, d: _native.ImageDesc) -> None:
+        d.kind, d.lens, d.height, d.width = self.kind, self.lens, self.height, self.width
+        d.fov, d.f_distance = float(self.fov), float(self.f_distance)
+
+
+@dataclass(frozen=True)
+class RayPlan:
+    """Lazy description of a coordinate map: output geometry + rotation matrices in order."""
+
+    out: ImageGeometry
+    rotations: Tuple[Tuple[float, ...], ...] = field(default_factory=tuple)
+
+    def rotated(self, matrix) -> "RayPlan":
+        m = tuple(float(v) for v in np.asarray(matrix, dtype=np.float64).reshape(9))
+        return RayPlan(self.out, self.rotations + (m,))
+
+    @property
+    def shape(self):
+        return (self.out.height, self.out.output_width, 3)
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "photonbend_b200 needs a CUDA device (B200, sm_100a): there is no CPU fallback"
+        )
+    return torch
+
+
+def _stream_ptr(torch) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _remap_desc(rays: RayPlan, src: ImageGeometry, channels: int) -> _native.RemapDesc:
+    if len(rays.rotations) > _native.PB_MAX_ROTATIONS:
+        raise _native.NativeError(_native.PB_ERR_TOO_MANY_ROTATIONS, "too many rotations to fuse")
+    d = _native.RemapDesc()
+    rays.out.fill(d.out)
+    src.fill(d.src)
+    d.channels = channels
+    d.n_rotations = len(rays.rotations)
+    for k, m in enumerate(rays.rotations):
+        for e in range(9):
+            d.rotations[k][e] = m[e]
+    return d
+
+
+# ----------------------------------------------------------------------------- image plumbing
+
+
+def is_torch_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def image_layout(image) -> Tuple[int, int, int, bool]:
+    """(height, width, channels, had_channel_axis) of an HWC / HW uint8 image."""
+    shape = tuple(image.shape)
+    if len(shape) == 2:
+        return shape[0], shape[1], 1, False
+    if len(shape) == 3:
+        return shape[0], shape[1], shape[2], True
+    raise ValueError(f"expected an (H, W, C) or (H, W) image, got shape {shape}")
+
+
+def _check_u8(image) -> None:
+    name = str(image.dtype)
+    if name not in ("uint8", "torch.uint8"):
+        raise NotImplementedError(f"only uint8 images are supported by the B200 path (got {name})")
+
+
+def to_device_u8(image):
+    """uint8 image (numpy / torch CPU / torch CUDA) -> contiguous CUDA tensor (async H2D on the
+    current stream; pinned host memory makes it a true async copy)."""
+    torch = _torch()
+    _check_u8(image)
+    if is_torch_tensor(image):
+        t = image
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(image))
+    if not t.is_cuda:
+        t = t.to("cuda", non_blocking=True)
+    return t.contiguous()
+
+
+def from_device_like(result, like, out=None):
+    """Hand a CUDA result back in the flavour of ``like`` (numpy -> numpy, torch CPU -> torch
+    CPU, torch CUDA -> the CUDA tensor itself).  ``out`` may be a preallocated (ideally pinned)
+    destination of the same flavour."""
+    torch = _torch()
+    if is_torch_tensor(like) and like.is_cuda:
+        if out is not None:
+            out.copy_(result)
+            return out
+        return result
+    if out is not None:
+        host = out if is_torch_tensor(out) else torch.from_numpy(out)
+        host.copy_(result, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out
+    host = result.cpu()
+    return host if is_torch_tensor(like) else host.numpy()
+
+
+# ----------------------------------------------------------------------------- calls
+
+
+def remap_device(rays: RayPlan, src: ImageGeometry, src_dev, out_dev=None):
+    """Fused remap on device tensors.  src_dev: uint8 CUDA tensor (H, W[, C]) or a batch
+    (N, H, W, C); returns (and fills) the uint8 CUDA output tensor."""
+    torch = _torch()
+    lib = _native.load()
+    batched = src_dev.dim() == 4
+    frames = src_dev.shape[0] if batched else 1
+    h, w, c, had_c = image_layout(src_dev[0] if batched else src_dev)
+    if (h, w) != (src.height, src.width):
+        raise ValueError(f"source image is {h}x{w} but its geometry says {src.height}x{src.width}")
+    oh, ow = rays.out.height, rays.out.output_width
+    out_shape = (oh, ow, c) if had_c else (oh, ow)
+    if batched:
+        out_shape = (frames,) + out_shape
+    if out_dev is None:
+        out_dev = torch.empty(out_shape, dtype=torch.uint8, device=src_dev.device)
+    elif tuple(out_dev.shape) != out_shape or not out_dev.is_contiguous() or out_dev.dtype != torch.uint8:
+        raise ValueError(f"out must be a contiguous uint8 tensor of shape {out_shape}")
+    desc = _remap_desc(rays, src, c)
+    with torch.cuda.device(src_dev.device):
+        _native.check(lib.pb_remap_u8(
+            ctypes.byref(desc),
+            ctypes.c_void_p(src_dev.data_ptr()), ctypes.c_int64(h * w * c),
+            ctypes.c_void_p(out_dev.data_ptr()), ctypes.c_int64(oh * ow * c),
+            ctypes.c_int32(frames), _stream_ptr(torch)))
+    return out_dev
+
+
+def materialize_map_device(rays: RayPlan):
+    """float64 CUDA tensor (H, W, 3) of the coordinate map described by ``rays``."""
+    torch = _torch()
+    lib = _native.load()
+    fused = RayPlan(rays.out, rays.rotations[: _native.PB_MAX_ROTATIONS])
+    rest = rays.rotations[_native.PB_MAX_ROTATIONS:]
+    cmap = torch.empty(rays.shape, dtype=torch.float64, device="cuda")
+    desc = _remap_desc(fused, fused.out, 1)
+    _native.check(lib.pb_materialize_map_f64(ctypes.byref(desc), ctypes.c_void_p(cmap.data_ptr()),
+                                             _stream_ptr(torch)))
+    for m in rest:
+        cmap = rotate_map_device(cmap, m)
+    return cmap
+
+
+def rotate_map_device(cmap_dev, matrix):
+    """Rotation.rotate_coordinate_map on a float64 CUDA map; zeroes the invalid entries of
+    ``cmap_dev`` in place like the reference (rotation.py:124-125) and returns the new map."""
+    torch = _torch()
+    lib = _native.load()
+    if cmap_dev.dtype != torch.float64 or cmap_dev.shape[-1] != 3 or not cmap_dev.is_contiguous():
+        raise ValueError("coordinate map must be a contiguous float64 (..., 3) tensor")
+    out = torch.empty_like(cmap_dev)
+    mat = (ctypes.c_double * 9)(*[float(v) for v in np.asarray(matrix, dtype=np.float64).reshape(9)])
+    with torch.cuda.device(cmap_dev.device):
+        _native.check(lib.pb_rotate_map_f64(mat, ctypes.c_void_p(cmap_dev.data_ptr()),
+                                            ctypes.c_void_p(out.data_ptr()),
+                                            ctypes.c_int64(cmap_dev.numel() // 3), _stream_ptr(torch)))
+    return out
+
+
+def gather_from_map_device(src: ImageGeometry, cmap_dev, src_dev, out_dev=None):
+    """process_coordinate_map on an explicit float64 CUDA map."""
+    torch = _torch()
+    lib = _native.load()
+    h, w, c, had_c = image_layout(src_dev)
+    if (h, w) != (src.height, src.width):
+        raise ValueError(f"source image is {h}x{w} but its geometry says {src.height}x{src.width}")
+    if cmap_dev.dim() != 3 or cmap_dev.shape[2] != 3 or cmap_dev.dtype != torch.float64:
+        raise ValueError("coordinate map must be float64 of shape (H, W, 3)")
+    if not cmap_dev.is_contiguous():
+        raise ValueError("coordinate map must be contiguous")
+    mh, mw = cmap_dev.shape[0], cmap_dev.shape[1]
+    out_shape = (mh, mw, c) if had_c else (mh, mw)
+    if out_dev is None:
+        out_dev = torch.empty(out_shape, dtype=torch.uint8, device=src_dev.device)
+    d = _native.ImageDesc()
+    src.fill(d)
+    with torch.cuda.device(src_dev.device):
+        _native.check(lib.pb_gather_from_map_u8(
+            ctypes.byref(d), ctypes.c_int32(c), ctypes.c_void_p(cmap_dev.data_ptr()),
+            ctypes.c_int32(mh), ctypes.c_int32(mw), ctypes.c_void_p(src_dev.data_ptr()),
+            ctypes.c_void_p(out_dev.data_ptr()), _stream_ptr(torch)))
+    return out_dev
