@@ -16,7 +16,9 @@
  *
  * Conventions
  *  - every pointer marked "device" is a CUDA device pointer on the CURRENT device; the caller
- *    allocates and owns every buffer; the library allocates nothing that outlives a call;
+ *    allocates and owns every buffer; the library allocates nothing that outlives a call, except
+ *    the small tables owned by a pb_plan (see below);
+ *  - source images may have at most 32767 rows and 65535 columns;
  *  - images are uint8, HWC, tightly packed (row pitch = width * channels);
  *  - coordinate maps are float64 (H, W, 3) = (latitude, longitude, invalid != 0), tightly packed
  *    (photonbend/core/__init__.py:42-49);
@@ -97,6 +99,22 @@ int32_t pb_output_width(const pb_image_desc *out);
  */
 int pb_remap_u8(const pb_remap_desc *desc, const uint8_t *src, int64_t src_frame_stride,
                 uint8_t *dst, int64_t dst_frame_stride, int32_t n_frames, void *stream);
+
+/*
+ * Plans.  A plan is one validated geometry together with everything derived from it: the host
+ * constants and, for an un-rotated equirect output (the video case, BASELINE config 5), small
+ * separable device tables (cos/sin of each column's longitude, lens radius of each row's
+ * latitude; 16*W + 32*H bytes) that the kernel would otherwise rebuild per call.  pb_remap_u8 is
+ * pb_plan_create + pb_plan_remap_u8 + pb_plan_destroy with the tables in a transient
+ * stream-ordered allocation.  The tables are the only device memory the library ever owns; they
+ * live on the device that was current at pb_plan_create and die with pb_plan_destroy.
+ * pb_plan_create enqueues the table kernel on `stream`; use the plan on that stream or after it.
+ */
+typedef struct pb_plan pb_plan;
+int pb_plan_create(const pb_remap_desc *desc, void *stream, pb_plan **plan);
+int pb_plan_remap_u8(const pb_plan *plan, const uint8_t *src, int64_t src_frame_stride, uint8_t *dst,
+                     int64_t dst_frame_stride, int32_t n_frames, void *stream);
+void pb_plan_destroy(pb_plan *plan);
 
 /*
  * get_coordinate_map() followed by desc->n_rotations rotate_coordinate_map() calls, written to

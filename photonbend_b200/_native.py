@@ -30,6 +30,9 @@ EXPORTS = (
     "pb_last_error",
     "pb_output_width",
     "pb_remap_u8",
+    "pb_plan_create",
+    "pb_plan_remap_u8",
+    "pb_plan_destroy",
     "pb_materialize_map_f64",
     "pb_rotate_map_f64",
     "pb_gather_from_map_u8",
@@ -87,6 +90,12 @@ def load():
     lib.pb_output_width.argtypes = [ctypes.POINTER(ImageDesc)]
     lib.pb_remap_u8.restype = ctypes.c_int
     lib.pb_remap_u8.argtypes = [ctypes.POINTER(RemapDesc), vp, i64, vp, i64, i32, vp]
+    lib.pb_plan_create.restype = ctypes.c_int
+    lib.pb_plan_create.argtypes = [ctypes.POINTER(RemapDesc), vp, ctypes.POINTER(vp)]
+    lib.pb_plan_remap_u8.restype = ctypes.c_int
+    lib.pb_plan_remap_u8.argtypes = [vp, vp, i64, vp, i64, i32, vp]
+    lib.pb_plan_destroy.restype = None
+    lib.pb_plan_destroy.argtypes = [vp]
     lib.pb_materialize_map_f64.restype = ctypes.c_int
     lib.pb_materialize_map_f64.argtypes = [ctypes.POINTER(RemapDesc), vp, vp]
     lib.pb_rotate_map_f64.restype = ctypes.c_int

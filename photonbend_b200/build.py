@@ -18,7 +18,8 @@ REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_PATH = os.path.join(PKG, "libpbremap.so")
 SOURCES = [os.path.join(CSRC, "pb_remap.cu")]
-HEADERS = [os.path.join(CSRC, "pb_device.cuh"), os.path.join(REPO, "include", "pb_remap.h")]
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [
+    os.path.join(REPO, "include", "pb_remap.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

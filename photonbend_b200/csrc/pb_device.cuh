@@ -170,29 +170,50 @@ __device__ __forceinline__ Ray rotate_ray(Ray in, const double* __restrict__ m) 
 
 // ---------------------------------------------------------------------------------- source lookup
 
-// What one output pixel reads: up to two source pixels (linear pixel offsets, -1 = black) and
-// their float64 weights.  Camera / equirect sources only use slot 0 with weight 1.
+// What one output pixel reads: up to two source pixels, each as packed coordinates
+// (row << 16 | column, column already including the half offset / mirror of a double image;
+// -1 = none, i.e. black) and their float64 weights.  Camera / equirect sources only use slot 0.
 struct Lookup {
-    int off0, off1;
+    int xy0, xy1;
     double w0, w1;
-    bool blend;  // double source: out = wrap_u8(p0*w0 + p1*w1)
 };
 
-// a9 projection.py:247-274 + 223-231: truncation toward zero BEFORE the bounds test, so a
-// coordinate in (-1, 0) lands on index 0 and is valid; NaN/inf are "problem positions".
-__device__ __forceinline__ int camera_offset(int lens, double f, double rect_limit, int h, int w,
-                                             double cy, double cx, double lat, double lon,
-                                             int row_pitch_px, int col0, bool flip) {
+constexpr int kNoPixel = -1;
+
+// ndarray.astype(int) followed by the bounds test of projection.py:223-231, for one coordinate:
+// truncation toward zero BEFORE the test, so a coordinate in (-1, 0) lands on index 0 and is
+// valid; NaN / inf / anything outside [0, n) is a "problem position" (-1).
+// |v| + 2^52 rounded toward zero leaves trunc(|v|) in the low mantissa word (one DADD instead
+// of a slow F2I.F64 conversion).
+__device__ __forceinline__ int trunc_index(double v, int n) {
+    const int hi = __double2hiint(v);
+    const unsigned ahi = (unsigned)hi & 0x7fffffffu;
+    const int idx = __double2loint(__dadd_rz(fabs(v), 4503599627370496.0));
+    const bool ok = ahi < 0x41E00000u /* |v| < 2^31, not NaN */ && (unsigned)idx < (unsigned)n &&
+                    !(hi < 0 && idx != 0);
+    return ok ? idx : -1;
+}
+
+__device__ __forceinline__ int pack_xy(int px, int py, int col0, int w, bool flip) {
+    if ((px | py) < 0) return kNoPixel;
+    return (py << 16) | (col0 + (flip ? (w - 1 - px) : px));
+}
+
+// a9 projection.py:247-274 + 223-231 with the radius already known: cos/sin of the longitude
+// and dist = forward_lens(lat) * f_distance.
+__device__ __forceinline__ int camera_xy_from(double c, double s, double dist, int h, int w, double cy,
+                                              double cx, int col0, bool flip) {
+    const double fx = __dadd_rn(__dmul_rn(c, dist), cx);
+    const double fy = __dadd_rn(__dmul_rn(__dmul_rn(s, dist), -1.0), cy);
+    return pack_xy(trunc_index(fx, w), trunc_index(fy, h), col0, w, flip);
+}
+
+__device__ __forceinline__ int camera_xy(int lens, double f, double rect_limit, int h, int w, double cy,
+                                         double cx, double lat, double lon, int col0, bool flip) {
     const double dist = __dmul_rn(lens_forward(lens, lat, rect_limit), f);
     double s, c;
     sincos(lon, &s, &c);
-    const double fx = __dadd_rn(__dmul_rn(c, dist), cx);
-    const double fy = __dadd_rn(__dmul_rn(__dmul_rn(s, dist), -1.0), cy);
-    if (!(fabs(fx) < 2147483648.0) || !(fabs(fy) < 2147483648.0)) return -1;
-    const int px = __double2int_rz(fx);
-    const int py = __double2int_rz(fy);
-    if (px < 0 || px >= w || py < 0 || py >= h) return -1;
-    return py * row_pitch_px + col0 + (flip ? (w - 1 - px) : px);
+    return camera_xy_from(c, s, dist, h, w, cy, cx, col0, flip);
 }
 
 // a10 projection.py:439-456
@@ -201,44 +222,47 @@ __device__ __forceinline__ double merge_weight(const SrcGeom& s, double lat) {
     return 1.0;
 }
 
+// a11 projection.py:542-545 for one axis: trunc(v) mod n with Python's sign convention
+__device__ __forceinline__ int wrap_index(double v, int n) {
+    if (v >= 0.0 && v < 2147483648.0) {
+        int t = __double2loint(__dadd_rz(v, 4503599627370496.0));
+        if (t >= n) t = (t < 2 * n) ? t - n : t % n;
+        return t;
+    }
+    return (int)floor_mod(trunc_i64(v), (long long)n);
+}
+
 template <int SRC_KIND>
 __device__ __forceinline__ Lookup source_lookup(const SrcGeom& s, Ray r) {
     Lookup L;
-    L.off0 = L.off1 = -1;
+    L.xy0 = L.xy1 = kNoPixel;
     L.w0 = L.w1 = 1.0;
-    L.blend = false;
     if (r.invalid) return L;
     if (SRC_KIND == PB_KIND_CAMERA) {
-        L.off0 = camera_offset(s.lens, s.f, s.rect_limit, s.H, s.W, s.cy, s.cx, r.lat, r.lon, s.W, 0, false);
+        L.xy0 = camera_xy(s.lens, s.f, s.rect_limit, s.H, s.W, s.cy, s.cx, r.lat, r.lon, 0, false);
     } else if (SRC_KIND == PB_KIND_EQUIRECT) {
         // a11 projection.py:515-547: true division, truncation, Python-sign modulo
-        const double frow = __ddiv_rn(r.lat, s.seg_h);
-        const double fcol = __dadd_rn(__ddiv_rn(r.lon, s.seg_w), s.half_w);
-        int row, col;
-        if (frow >= 0.0 && frow < 2147483648.0) {
-            row = __double2int_rz(frow);
-            if (row >= s.H) row = (row < 2 * s.H) ? row - s.H : row % s.H;
-        } else {
-            row = (int)floor_mod(trunc_i64(frow), (long long)s.H);
-        }
-        if (fcol >= 0.0 && fcol < 2147483648.0) {
-            col = __double2int_rz(fcol);
-            if (col >= s.W) col = (col < 2 * s.W) ? col - s.W : col % s.W;
-        } else {
-            col = (int)floor_mod(trunc_i64(fcol), (long long)s.W);
-        }
-        L.off0 = row * s.W + col;
+        const int row = wrap_index(__ddiv_rn(r.lat, s.seg_h), s.H);
+        const int col = wrap_index(__dadd_rn(__ddiv_rn(r.lon, s.seg_w), s.half_w), s.W);
+        L.xy0 = (row << 16) | col;
     } else {
         // a10 projection.py:408-462: both halves are sampled as plain cameras of magnitude H/2
         const double lat_l = r.lat;
         const double lat_r = __dadd_rn(__dmul_rn(r.lat, -1.0), kPi);
-        L.off0 = camera_offset(s.lens, s.f, s.rect_limit, s.H, s.wl, s.cy, s.cxl, lat_l, r.lon, s.W, 0, false);
-        L.off1 = camera_offset(s.lens, s.f, s.rect_limit, s.H, s.wr, s.cy, s.cxr, lat_r, r.lon, s.W, s.wl, true);
+        double sn, cs;
+        sincos(r.lon, &sn, &cs);
+        const double dist_l = __dmul_rn(lens_forward(s.lens, lat_l, s.rect_limit), s.f);
+        const double dist_r = __dmul_rn(lens_forward(s.lens, lat_r, s.rect_limit), s.f);
+        L.xy0 = camera_xy_from(cs, sn, dist_l, s.H, s.wl, s.cy, s.cxl, 0, false);
+        L.xy1 = camera_xy_from(cs, sn, dist_r, s.H, s.wr, s.cy, s.cxr, s.wl, true);
         L.w0 = merge_weight(s, lat_l);
         L.w1 = merge_weight(s, lat_r);
-        L.blend = true;
     }
     return L;
+}
+
+__device__ __forceinline__ int xy_to_offset(int xy, int width) {
+    return xy < 0 ? -1 : (xy >> 16) * width + (xy & 0xffff);
 }
 
 // (left*wl + right*wr).astype(np.uint8): truncate, keep the low byte  (projection.py:459)

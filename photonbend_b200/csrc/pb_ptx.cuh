@@ -1,0 +1,99 @@
+// pb_ptx.cuh -- thin inline-PTX wrappers (sm_100a): mbarrier, TMA bulk copies (cp.async.bulk,
+// SASS UBLKCP), async-proxy fences.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pb {
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbarrier_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+
+// make mbarrier.init visible to the async proxy (TMA) before the first bulk copy targets it
+__device__ __forceinline__ void fence_mbarrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbarrier_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ bool mbarrier_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbarrier_try_wait(bar, parity)) {
+    }
+}
+
+// global -> shared bulk copy (TMA, 1-D): 16-byte aligned addresses, size a multiple of 16;
+// completion is signalled on `bar` as a transaction of `bytes` bytes.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// shared -> global bulk copy (TMA, 1-D), tracked by the per-thread bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_addr(smem_src)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+
+// wait until the bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// wait until at most one bulk store group of this thread is still reading shared memory
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+// TMA tensor-map (cuTensorMapEncodeTiled) 3-D box load: global -> shared, completion on `bar`.
+// Coordinates are in elements of the map, innermost first; out-of-bounds parts of the box are
+// zero-filled by the hardware.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_addr(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar))
+        : "memory");
+}
+
+// TMA tensor-map 3-D box store: shared -> global (clipped to the tensor's bounds), bulk async-group
+__device__ __forceinline__ void tma_store_3d(const void* tmap, int c0, int c1, int c2, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(smem_src))
+                 : "memory");
+}
+
+__device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+// generic-proxy writes to shared memory -> visible to the async proxy (before a bulk store)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace ptx
+}  // namespace pb

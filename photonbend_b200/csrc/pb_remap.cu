@@ -6,9 +6,11 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 
 #include "pb_device.cuh"
+#include "pb_tiled.cuh"
 
 namespace pb {
 
@@ -155,25 +157,27 @@ __global__ void __launch_bounds__(256) remap_generic_kernel(const __grid_constan
     Ray r = output_ray<OUT_KIND>(a.out, i, j);
     for (int k = 0; k < a.rot.n; ++k) r = rotate_ray(r, a.rot.m[k]);
     const Lookup L = source_lookup<SRC_KIND>(a.src, r);
+    const int off0 = xy_to_offset(L.xy0, a.src.W);
+    const int off1 = xy_to_offset(L.xy1, a.src.W);
 
     const long long dst_off = ((long long)i * a.out.W + j) * C;
     for (int f = 0; f < a.n_frames; ++f) {
         const unsigned char* __restrict__ sp = a.src_px + f * a.src_frame_stride;
         unsigned char* __restrict__ dp = a.dst_px + f * a.dst_frame_stride + dst_off;
         if (SRC_KIND != PB_KIND_DOUBLE) {
-            if (L.off0 >= 0) copy_px<C>(dp, sp + (long long)L.off0 * C);
+            if (off0 >= 0) copy_px<C>(dp, sp + (long long)off0 * C);
             else zero_px<C>(dp);
         } else {
             if (r.invalid) {
                 zero_px<C>(dp);
                 continue;
             }
-            const unsigned char* p0 = sp + (long long)(L.off0 >= 0 ? L.off0 : 0) * C;
-            const unsigned char* p1 = sp + (long long)(L.off1 >= 0 ? L.off1 : 0) * C;
+            const unsigned char* p0 = sp + (long long)(off0 >= 0 ? off0 : 0) * C;
+            const unsigned char* p1 = sp + (long long)(off1 >= 0 ? off1 : 0) * C;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const unsigned v0 = L.off0 >= 0 ? __ldg(p0 + c) : 0u;
-                const unsigned v1 = L.off1 >= 0 ? __ldg(p1 + c) : 0u;
+                const unsigned v0 = off0 >= 0 ? __ldg(p0 + c) : 0u;
+                const unsigned v1 = off1 >= 0 ? __ldg(p1 + c) : 0u;
                 dp[c] = blend_u8(v0, L.w0, v1, L.w1);
             }
         }
@@ -234,21 +238,23 @@ __global__ void __launch_bounds__(256) gather_from_map_kernel(const __grid_const
         map[p * 3 + 1] = 0.0;
     }
     const Lookup L = source_lookup<SRC_KIND>(src, r);
+    const int off0 = xy_to_offset(L.xy0, src.W);
+    const int off1 = xy_to_offset(L.xy1, src.W);
     unsigned char* dp = dst + p * C;
     if (SRC_KIND != PB_KIND_DOUBLE) {
-        if (L.off0 >= 0) copy_px<C>(dp, sp + (long long)L.off0 * C);
+        if (off0 >= 0) copy_px<C>(dp, sp + (long long)off0 * C);
         else zero_px<C>(dp);
     } else {
         if (r.invalid) {
             zero_px<C>(dp);
             return;
         }
-        const unsigned char* p0 = sp + (long long)(L.off0 >= 0 ? L.off0 : 0) * C;
-        const unsigned char* p1 = sp + (long long)(L.off1 >= 0 ? L.off1 : 0) * C;
+        const unsigned char* p0 = sp + (long long)(off0 >= 0 ? off0 : 0) * C;
+        const unsigned char* p1 = sp + (long long)(off1 >= 0 ? off1 : 0) * C;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const unsigned v0 = L.off0 >= 0 ? __ldg(p0 + c) : 0u;
-            const unsigned v1 = L.off1 >= 0 ? __ldg(p1 + c) : 0u;
+            const unsigned v0 = off0 >= 0 ? __ldg(p0 + c) : 0u;
+            const unsigned v1 = off1 >= 0 ? __ldg(p1 + c) : 0u;
             dp[c] = blend_u8(v0, L.w0, v1, L.w1);
         }
     }
@@ -298,6 +304,189 @@ static void launch_gather_c(const SrcGeom& s, double* map, long long n, const un
     }
 }
 
+// ------------------------------------------------------------------------------------ tiled path
+
+// cuTensorMapEncodeTiled, fetched through the runtime so that libcuda is not a link dependency
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// 3-D map over a batch of HWC uint8 frames seen as rows of bytes: {row bytes, rows, frames}
+static bool encode_frames_map(CUtensorMap* map, const void* base, long long pitch, int rows, int frames,
+                              long long frame_stride, int elem_bytes, int box_bytes, int box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)(pitch / elem_bytes), (cuuint64_t)rows, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)(frames > 1 ? frame_stride : pitch * rows)};
+    const cuuint32_t box[3] = {(cuuint32_t)(box_bytes / elem_bytes), (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    return enc(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+constexpr int kMaxTiledSmem = 200 * 1024;
+
+template <int OUT_KIND, int SRC_KIND, int MODE>
+static cudaError_t launch_tiled_one(const TiledArgs& a, cudaStream_t st) {
+    const int smem = tiled_smem_bytes<SRC_KIND, MODE>(a.stage_pitch, a.stage_boxes, a.n_buffers);
+    static bool configured = false;  // per instantiation; the attribute is per device function
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTiledSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((a.out.W + kTileW - 1) / kTileW, (a.out.H + kTileH - 1) / kTileH);
+    remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE><<<grid, kTileThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int OUT_KIND>
+static cudaError_t launch_tiled_generic_s(const TiledArgs& a, cudaStream_t st) {
+    switch (a.src.kind) {
+        case PB_KIND_CAMERA: return launch_tiled_one<OUT_KIND, PB_KIND_CAMERA, 0>(a, st);
+        case PB_KIND_DOUBLE: return launch_tiled_one<OUT_KIND, PB_KIND_DOUBLE, 0>(a, st);
+        default: return launch_tiled_one<OUT_KIND, PB_KIND_EQUIRECT, 0>(a, st);
+    }
+}
+
+static cudaError_t launch_tiled(const TiledArgs& a, bool separable, cudaStream_t st) {
+    if (separable) {
+        if (a.src.kind == PB_KIND_CAMERA) return launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_CAMERA, 1>(a, st);
+        return launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1>(a, st);
+    }
+    switch (a.out.kind) {
+        case PB_KIND_CAMERA: return launch_tiled_generic_s<PB_KIND_CAMERA>(a, st);
+        case PB_KIND_DOUBLE: return launch_tiled_generic_s<PB_KIND_DOUBLE>(a, st);
+        default: return launch_tiled_generic_s<PB_KIND_EQUIRECT>(a, st);
+    }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace pb
+
+// A plan: one validated geometry with everything derived from it (host constants, and for an
+// un-rotated equirect output the separable device tables).
+struct pb_plan {
+    pb_remap_desc desc;
+    pb::OutGeom out;
+    pb::SrcGeom src;
+    pb::Rotations rot;
+    bool separable;      // un-rotated equirect output, camera / double source
+    int stage_pitch;     // bytes per staged source row (TMA box width)
+    int stage_boxes;     // 16-row TMA boxes per stage buffer
+    double* tables;      // device: col_tab [W][2] then row_tab [H][4]; null unless separable
+    int device;
+};
+
+namespace pb {
+
+static int validate_desc(const pb_remap_desc* desc, const char* who) {
+    if (!desc) return fail(PB_ERR_INVALID_ARGUMENT, std::string(who) + ": null descriptor");
+    if (int rc = check_image(desc->out, "out")) return rc;
+    if (int rc = check_image(desc->src, "src")) return rc;
+    if (desc->src.height > 32767 || desc->src.width > 65535)
+        return fail(PB_ERR_UNSUPPORTED, std::string(who) + ": source larger than 32767 rows x 65535 columns");
+    if (desc->channels < 1 || desc->channels > 4)
+        return fail(PB_ERR_UNSUPPORTED, std::string(who) + ": channels must be 1..4");
+    if (desc->n_rotations < 0) return fail(PB_ERR_INVALID_ARGUMENT, std::string(who) + ": negative n_rotations");
+    if (desc->n_rotations > PB_MAX_ROTATIONS)
+        return fail(PB_ERR_TOO_MANY_ROTATIONS, std::string(who) + ": more than PB_MAX_ROTATIONS rotations");
+    return PB_OK;
+}
+
+static void plan_init(pb_plan& p, const pb_remap_desc& d) {
+    p.desc = d;
+    p.out = derive_out(d.out);
+    p.src = derive_src(d.src, d.channels);
+    p.rot.n = d.n_rotations;
+    std::memcpy(p.rot.m, d.rotations, sizeof(p.rot.m));
+    p.separable = d.out.kind == PB_KIND_EQUIRECT && d.n_rotations == 0 && d.src.kind != PB_KIND_EQUIRECT &&
+                  d.channels == 3;
+    p.stage_pitch = 288;  // 96 source pixels
+    p.stage_boxes = 6;    // 96 source rows
+    p.tables = nullptr;
+    p.device = -1;
+}
+
+static size_t table_doubles(const pb_plan& p) { return 2 * (size_t)p.out.W + 4 * (size_t)p.out.H; }
+
+static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st) {
+    const int n = p.out.W > p.out.H ? p.out.W : p.out.H;
+    pb_tables_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.out, p.src, tables, tables + 2 * (size_t)p.out.W);
+    return cudaGetLastError();
+}
+
+// tables: the plan's own, a transient stream-ordered allocation, or null (generic rays)
+static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, int64_t src_frame_stride,
+                    uint8_t* dst, int64_t dst_frame_stride, int32_t n_frames, cudaStream_t st) {
+    const int C = p.desc.channels;
+    const long long src_pitch = (long long)p.src.W * C, dst_pitch = (long long)p.out.W * C;
+    const bool multi = n_frames > 1;
+    const bool tiled_ok = C == 3 && aligned16(src) && aligned16(dst) && src_pitch % 16 == 0 && dst_pitch % 16 == 0 &&
+                          (!multi || (src_frame_stride % 16 == 0 && dst_frame_stride % 16 == 0)) &&
+                          src_pitch * p.src.H < (1LL << 31);
+    if (tiled_ok) {
+        TiledArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.out = p.out;
+        a.src = p.src;
+        a.rot = p.rot;
+        a.col_tab = tables;
+        a.row_tab = tables ? tables + 2 * (size_t)p.out.W : nullptr;
+        a.src_px = src;
+        a.src_frame_stride = src_frame_stride;
+        a.n_frames = n_frames;
+        a.src_pitch = (int)src_pitch;
+        // stage geometry: one column of 16-row TMA boxes per slot
+        const bool dbl = p.src.kind == PB_KIND_DOUBLE;
+        a.stage_pitch = p.stage_pitch;
+        a.stage_boxes = p.stage_boxes;
+        a.n_buffers = (multi && !dbl) ? 2 : 1;
+        if (encode_frames_map(&a.src_map, src, src_pitch, p.src.H, n_frames, src_frame_stride, 2, a.stage_pitch,
+                              kBoxRows) &&
+            encode_frames_map(&a.dst_map, dst, dst_pitch, p.out.H, n_frames, dst_frame_stride, 1, kOutRowBytes,
+                              kTileH)) {
+            cudaError_t e = launch_tiled(a, p.separable && tables != nullptr, st);
+            if (e != cudaSuccess) return cuda_fail(e, "tiled remap launch");
+            return PB_OK;
+        }
+        // no tensor-map encoder in this driver: the generic kernel below needs none
+    }
+    RemapArgs a;
+    a.out = p.out;
+    a.src = p.src;
+    a.rot = p.rot;
+    a.src_px = src;
+    a.dst_px = dst;
+    a.src_frame_stride = src_frame_stride;
+    a.dst_frame_stride = dst_frame_stride;
+    a.n_frames = n_frames;
+    launch_generic(a, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "generic remap launch");
+    return PB_OK;
+}
+
 }  // namespace pb
 
 // ------------------------------------------------------------------------------------ C ABI
@@ -317,31 +506,69 @@ int32_t pb_output_width(const pb_image_desc* out) {
 
 int pb_remap_u8(const pb_remap_desc* desc, const uint8_t* src, int64_t src_frame_stride, uint8_t* dst,
                 int64_t dst_frame_stride, int32_t n_frames, void* stream) {
-    if (!desc || !src || !dst) return fail(PB_ERR_INVALID_ARGUMENT, "pb_remap_u8: null pointer");
-    if (int rc = check_image(desc->out, "out")) return rc;
-    if (int rc = check_image(desc->src, "src")) return rc;
-    if (desc->channels < 1 || desc->channels > 4)
-        return fail(PB_ERR_UNSUPPORTED, "pb_remap_u8: channels must be 1..4");
-    if (desc->n_rotations < 0) return fail(PB_ERR_INVALID_ARGUMENT, "pb_remap_u8: negative n_rotations");
-    if (desc->n_rotations > PB_MAX_ROTATIONS)
-        return fail(PB_ERR_TOO_MANY_ROTATIONS, "pb_remap_u8: more than PB_MAX_ROTATIONS rotations");
+    if (!src || !dst) return fail(PB_ERR_INVALID_ARGUMENT, "pb_remap_u8: null pointer");
+    if (int rc = validate_desc(desc, "pb_remap_u8")) return rc;
     if (n_frames < 0) return fail(PB_ERR_INVALID_ARGUMENT, "pb_remap_u8: negative n_frames");
     if (n_frames == 0) return PB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    pb_plan p;
+    plan_init(p, *desc);
+    double* tables = nullptr;
+    if (p.separable) {
+        // transient, stream-ordered: nothing outlives the call
+        if (cudaMallocAsync((void**)&tables, table_doubles(p) * sizeof(double), st) != cudaSuccess) {
+            (void)cudaGetLastError();
+            tables = nullptr;  // no memory pool on this device: the generic rays need no tables
+        } else if (cudaError_t e = fill_tables(p, tables, st)) {
+            cudaFreeAsync(tables, st);
+            return cuda_fail(e, "pb_remap_u8 tables launch");
+        }
+    }
+    const int rc = plan_run(p, tables, src, src_frame_stride, dst, dst_frame_stride, n_frames, st);
+    if (tables) cudaFreeAsync(tables, st);
+    return rc;
+}
 
-    RemapArgs a;
-    a.out = derive_out(desc->out);
-    a.src = derive_src(desc->src, desc->channels);
-    a.rot.n = desc->n_rotations;
-    std::memcpy(a.rot.m, desc->rotations, sizeof(a.rot.m));
-    a.src_px = src;
-    a.dst_px = dst;
-    a.src_frame_stride = src_frame_stride;
-    a.dst_frame_stride = dst_frame_stride;
-    a.n_frames = n_frames;
-    launch_generic(a, (cudaStream_t)stream);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "pb_remap_u8 launch");
+int pb_plan_create(const pb_remap_desc* desc, void* stream, pb_plan** plan_out) {
+    if (!plan_out) return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_create: null plan pointer");
+    *plan_out = nullptr;
+    if (int rc = validate_desc(desc, "pb_plan_create")) return rc;
+    pb_plan* p = new (std::nothrow) pb_plan;
+    if (!p) return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_create: out of host memory");
+    plan_init(*p, *desc);
+    cudaError_t e = cudaGetDevice(&p->device);
+    if (e != cudaSuccess) {
+        delete p;
+        return cuda_fail(e, "pb_plan_create");
+    }
+    if (p->separable) {
+        e = cudaMalloc((void**)&p->tables, table_doubles(*p) * sizeof(double));
+        if (e == cudaSuccess) e = fill_tables(*p, p->tables, (cudaStream_t)stream);
+        if (e != cudaSuccess) {
+            if (p->tables) cudaFree(p->tables);
+            delete p;
+            return cuda_fail(e, "pb_plan_create tables");
+        }
+    }
+    *plan_out = p;
     return PB_OK;
+}
+
+int pb_plan_remap_u8(const pb_plan* plan, const uint8_t* src, int64_t src_frame_stride, uint8_t* dst,
+                     int64_t dst_frame_stride, int32_t n_frames, void* stream) {
+    if (!plan || !src || !dst) return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_remap_u8: null pointer");
+    if (n_frames < 0) return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_remap_u8: negative n_frames");
+    if (n_frames == 0) return PB_OK;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != plan->device)
+        return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_remap_u8: plan belongs to another device");
+    return plan_run(*plan, plan->tables, src, src_frame_stride, dst, dst_frame_stride, n_frames, (cudaStream_t)stream);
+}
+
+void pb_plan_destroy(pb_plan* plan) {
+    if (!plan) return;
+    if (plan->tables) cudaFree(plan->tables);
+    delete plan;
 }
 
 int pb_materialize_map_f64(const pb_remap_desc* desc, double* map, void* stream) {

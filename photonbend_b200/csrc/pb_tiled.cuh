@@ -1,0 +1,384 @@
+// pb_tiled.cuh -- the tiled remap kernel (sm_100a), C = 3 uint8 channels.
+//
+// One CTA = one 32 x 64 tile of the output image (the shape whose source footprint is most
+// compact for fisheye <-> equirect mappings), 256 threads, each thread owning two
+// "quads" (4 consecutive pixels of a row = 12 output bytes = three 32-bit words).
+//
+//   1. resolve   every thread resolves the source coordinates of its 8 pixels in float64
+//                registers -- either through the generic ray / rotate / lookup functions, or, for
+//                an un-rotated equirectangular output, from the separable tables (cos/sin of the
+//                column's longitude, lens radius of the row's latitude) that pb_tables_kernel wrote
+//                once per geometry.  No coordinate map ever exists in memory.
+//   2. footprint the CTA reduces the bounding rectangle of the source pixels its tile reads
+//                (warp redux + shared atomics), one rectangle per source "slot" (a double-fisheye
+//                source has two: left and right lens).
+//   3. stage     for every frame of the batch one elected thread pulls the rectangle into shared
+//                memory with TMA tensor-map box loads (cp.async.bulk.tensor, 16-row boxes, one
+//                mbarrier per stage buffer; the hardware zero-fills what hangs over the image
+//                border).  With several frames per launch the loads of frame f+1 are in flight
+//                while frame f is gathered (two stage buffers).  Tiles whose footprint does not
+//                fit (a pole, the +-pi seam of a panorama) gather straight from global memory.
+//   4. gather    threads pick their pixels out of shared memory (two aligned 32-bit loads + a
+//                funnel shift per pixel), blend the two slots where the source is a double
+//                fisheye, pack 4 pixels into 3 words and write them into the shared output tile.
+//   5. store     one TMA tensor-map box store drains the 32 x 64 tile to HBM (clipped by the
+//                hardware at the image border), overlapping the next frame's gather.
+//
+// Steps 1-2 run once per tile, steps 3-5 once per frame: a batch of frames that share a geometry
+// pays the float64 index math once.
+#pragma once
+
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through the runtime)
+
+#include "pb_device.cuh"
+#include "pb_ptx.cuh"
+
+namespace pb {
+
+constexpr int kTileW = 32;
+constexpr int kTileH = 64;
+constexpr int kTileThreads = 256;
+constexpr int kQuadsPerRow = kTileW / 4;                 // 8
+constexpr int kRowGroups = kTileThreads / kQuadsPerRow;  // 32
+constexpr int kRowsPerThread = kTileH / kRowGroups;      // 2
+constexpr int kPxPerThread = 4 * kRowsPerThread;         // 8
+constexpr int kOutRowBytes = kTileW * 3;                 // 96
+constexpr int kOutTileBytes = kOutRowBytes * kTileH;     // 6144
+constexpr int kBoxRows = 16;                             // rows per TMA box of the source map
+
+struct TiledArgs {
+    CUtensorMap src_map;  // u16 elements: {pitch/2, H, frames}, box {stage_pitch/2, 16, 1}
+    CUtensorMap dst_map;  // u8 elements:  {W*3, H, frames},   box {96, 64, 1}
+    OutGeom out;
+    SrcGeom src;
+    Rotations rot;
+    const double* col_tab;  // separable: [W][2]  (cos lon_j, sin lon_j)
+    const double* row_tab;  // separable: [H][4]  camera: (dist, -, -, -); double: (dist_l, dist_r, w_l, w_r)
+    const unsigned char* src_px;
+    long long src_frame_stride;
+    int n_frames;
+    int src_pitch;    // bytes per source row
+    int stage_pitch;  // bytes per staged row (= box width), multiple of 16
+    int stage_boxes;  // capacity of one stage buffer of one slot, in 16-row boxes
+    int n_buffers;    // 1, or 2 when frames are pipelined
+};
+
+// Separable tables for an un-rotated equirect output (a1) feeding a camera (a9) or double (a10)
+// source: everything that depends on the column only, or on the row only, evaluated with exactly
+// the expressions the per-pixel path uses.
+__global__ void __launch_bounds__(256) pb_tables_kernel(const __grid_constant__ OutGeom out,
+                                                        const __grid_constant__ SrcGeom src,
+                                                        double* __restrict__ col_tab,
+                                                        double* __restrict__ row_tab) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < out.W) {
+        const double lon = linspace_at(out.x_start, out.x_stop, out.x_step, out.W, t);
+        double s, c;
+        sincos(lon, &s, &c);
+        col_tab[2 * t + 0] = c;
+        col_tab[2 * t + 1] = s;
+    }
+    if (t < out.H) {
+        const double lat = linspace_at(out.y_start, out.y_stop, out.y_step, out.H, t);
+        double* r = row_tab + 4 * t;
+        if (src.kind == PB_KIND_DOUBLE) {
+            const double lat_r = __dadd_rn(__dmul_rn(lat, -1.0), kPi);
+            r[0] = __dmul_rn(lens_forward(src.lens, lat, src.rect_limit), src.f);
+            r[1] = __dmul_rn(lens_forward(src.lens, lat_r, src.rect_limit), src.f);
+            r[2] = merge_weight(src, lat);
+            r[3] = merge_weight(src, lat_r);
+        } else {
+            r[0] = __dmul_rn(lens_forward(src.lens, lat, src.rect_limit), src.f);
+            r[1] = 0.0;
+            r[2] = 1.0;
+            r[3] = 1.0;
+        }
+    }
+}
+
+struct TileShared {
+    uint64_t bar[2];  // one mbarrier per stage buffer
+    int min_x[2], max_x[2], min_y[2], max_y[2];
+};
+
+__device__ __forceinline__ unsigned pick_px(const unsigned char* __restrict__ stage, int b) {
+    // 3 bytes at byte offset b of the staged rectangle: two aligned words + funnel shift
+    const unsigned* w = reinterpret_cast<const unsigned*>(stage + (b & ~3));
+    return __funnelshift_r(w[0], w[1], (b & 3) * 8) & 0x00ffffffu;
+}
+
+__device__ __forceinline__ unsigned pick_px_global(const unsigned char* __restrict__ img, int b) {
+    return (unsigned)__ldg(img + b) | ((unsigned)__ldg(img + b + 1) << 8) | ((unsigned)__ldg(img + b + 2) << 16);
+}
+
+__device__ __forceinline__ unsigned blend_px(unsigned a, double wa, unsigned b, double wb) {
+    if (wa == 1.0 && wb == 1.0) return __vadd4(a, b) & 0x00ffffffu;  // exact: bytes add mod 256
+    unsigned r = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        r |= (unsigned)blend_u8((a >> (8 * c)) & 0xffu, wa, (b >> (8 * c)) & 0xffu, wb) << (8 * c);
+    return r;
+}
+
+// projection.py:223-231 + 254-259 for both coordinates of one camera sample, the way the tiled
+// kernel wants it: "0 <= trunc(v) < n" is "-1 < v < n" on the reals (NaN fails every compare).
+__device__ __forceinline__ int camera_xy_fast(double c, double s, double dist, int h, int w, double cy, double cx,
+                                              int col0, bool flip) {
+    const double fx = __dadd_rn(__dmul_rn(c, dist), cx);
+    const double fy = __dadd_rn(__dmul_rn(__dmul_rn(s, dist), -1.0), cy);
+    const bool ok = fx > -1.0 && fx < (double)w && fy > -1.0 && fy < (double)h;
+    const int px = __double2loint(__dadd_rz(fabs(fx), 4503599627370496.0));
+    const int py = __double2loint(__dadd_rz(fabs(fy), 4503599627370496.0));
+    return ok ? ((py << 16) | (col0 + (flip ? (w - 1 - px) : px))) : kNoPixel;
+}
+
+// MODE: 0 = generic per-pixel rays (any output, any rotations), 1 = separable tables
+template <int OUT_KIND, int SRC_KIND, int MODE>
+__global__ void __launch_bounds__(kTileThreads, (MODE == 1) ? 3 : 2)
+remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
+    constexpr int NSLOT = (SRC_KIND == PB_KIND_DOUBLE) ? 2 : 1;
+    constexpr int S1 = NSLOT - 1;  // index of the second slot (aliases the first when there is none)
+    constexpr bool DBL = (SRC_KIND == PB_KIND_DOUBLE);
+    constexpr bool WGT_IN_SMEM = DBL && MODE == 0;  // per-pixel weights live in shared memory
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    // [ out tiles: n_buffers x 6144 ][ stage: n_buffers x NSLOT x (boxes*16*pitch + 128) ][ TileShared ][ scratch ]
+    const int slot_bytes = a.stage_boxes * kBoxRows * a.stage_pitch + 128;  // + zeroed tail
+    unsigned char* out_tiles = smem;
+    unsigned char* stages = smem + a.n_buffers * kOutTileBytes;
+    TileShared* sh = reinterpret_cast<TileShared*>(stages + a.n_buffers * NSLOT * slot_bytes);
+    int* xy_scratch = reinterpret_cast<int*>(sh + 1);                        // MODE 0: [NSLOT][8][256]
+    double2* w_scratch = reinterpret_cast<double2*>(xy_scratch + NSLOT * kPxPerThread * kTileThreads);  // [8][256]
+
+    const int tid = threadIdx.x;
+    const int qc = tid & (kQuadsPerRow - 1);
+    const int rg = tid >> 3;
+    const int x0 = blockIdx.x * kTileW;
+    const int y0 = blockIdx.y * kTileH;
+    const int jx = x0 + 4 * qc;
+
+    if (tid == 0) {
+        ptx::prefetch_tensormap(&a.src_map);
+        ptx::prefetch_tensormap(&a.dst_map);
+        ptx::mbarrier_init(&sh->bar[0], 1);
+        ptx::mbarrier_init(&sh->bar[1], 1);
+        ptx::fence_mbarrier_init();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            sh->min_x[s] = 0x7fffffff;
+            sh->min_y[s] = 0x7fffffff;
+            sh->max_x[s] = -1;
+            sh->max_y[s] = -1;
+        }
+    }
+    // zeroed tail of every stage buffer: where pixels without a source read their black
+    if (tid < a.n_buffers * NSLOT * 8)
+        reinterpret_cast<int4*>(stages + (tid >> 3) * slot_bytes + slot_bytes - 128)[tid & 7] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+
+    // ---------------------------------------------------------------- 1. resolve  2. footprint
+    int loc[NSLOT][kPxPerThread];
+    double wrow[kRowsPerThread][2];  // separable double source: blend weights per row
+    int mnx[NSLOT], mny[NSLOT], mxx[NSLOT], mxy[NSLOT];
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        mnx[s] = mny[s] = 0x7fffffff;
+        mxx[s] = mxy[s] = -1;
+    }
+
+    if (MODE == 1) {
+        double2 cs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cs[k] = __ldg(reinterpret_cast<const double2*>(a.col_tab) + min(jx + k, a.out.W - 1));
+#pragma unroll
+        for (int q = 0; q < kRowsPerThread; ++q) {
+            // rows past the image edge repeat the last row: they widen nothing and TMA clips them
+            const int i = min(y0 + rg * kRowsPerThread + q, a.out.H - 1);
+            const double2 r01 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i);
+            if (DBL) {
+                const double2 r23 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i + 1);
+                wrow[q][0] = r23.x;
+                wrow[q][1] = r23.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (DBL) {
+                    loc[0][q * 4 + k] = camera_xy_fast(cs[k].x, cs[k].y, r01.x, a.src.H, a.src.wl, a.src.cy, a.src.cxl, 0, false);
+                    loc[S1][q * 4 + k] = camera_xy_fast(cs[k].x, cs[k].y, r01.y, a.src.H, a.src.wr, a.src.cy, a.src.cxr, a.src.wl, true);
+                } else {
+                    loc[0][q * 4 + k] = camera_xy_fast(cs[k].x, cs[k].y, r01.x, a.src.H, a.src.W, a.src.cy, a.src.cx, 0, false);
+                }
+            }
+        }
+    } else {
+        // generic rays: heavy float64 code, kept rolled (results parked in shared memory)
+#pragma unroll 1
+        for (int p = 0; p < kPxPerThread; ++p) {
+            const int i = min(y0 + rg * kRowsPerThread + (p >> 2), a.out.H - 1);
+            const int j = min(jx + (p & 3), a.out.W - 1);
+            Ray r = output_ray<OUT_KIND>(a.out, i, j);
+            for (int n = 0; n < a.rot.n; ++n) r = rotate_ray(r, a.rot.m[n]);
+            const Lookup L = source_lookup<SRC_KIND>(a.src, r);
+            xy_scratch[p * kTileThreads + tid] = L.xy0;
+            if (DBL) {
+                xy_scratch[(kPxPerThread + p) * kTileThreads + tid] = L.xy1;
+                w_scratch[p * kTileThreads + tid] = make_double2(L.w0, L.w1);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < kPxPerThread; ++p) {
+            loc[0][p] = xy_scratch[p * kTileThreads + tid];
+            if (DBL) loc[S1][p] = xy_scratch[(kPxPerThread + p) * kTileThreads + tid];
+        }
+    }
+
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+#pragma unroll
+        for (int p = 0; p < kPxPerThread; ++p) {
+            const int v = loc[s][p];
+            if (v >= 0) {
+                const int sx = v & 0xffff, sy = v >> 16;
+                mnx[s] = min(mnx[s], sx);
+                mxx[s] = max(mxx[s], sx);
+                mny[s] = min(mny[s], sy);
+                mxy[s] = max(mxy[s], sy);
+            }
+        }
+        mnx[s] = __reduce_min_sync(0xffffffffu, mnx[s]);
+        mny[s] = __reduce_min_sync(0xffffffffu, mny[s]);
+        mxx[s] = __reduce_max_sync(0xffffffffu, mxx[s]);
+        mxy[s] = __reduce_max_sync(0xffffffffu, mxy[s]);
+        if ((tid & 31) == 0 && mxx[s] >= 0) {
+            atomicMin(&sh->min_x[s], mnx[s]);
+            atomicMin(&sh->min_y[s], mny[s]);
+            atomicMax(&sh->max_x[s], mxx[s]);
+            atomicMax(&sh->max_y[s], mxy[s]);
+        }
+    }
+    __syncthreads();
+
+    // rectangle of slot s: rows [by0, by0 + 16*nbox), bytes [xb0, xb0 + stage_pitch) of each row
+    int by0[NSLOT], xb0[NSLOT], nbox[NSLOT];
+    bool staged = true, any = false;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+        by0[s] = xb0[s] = nbox[s] = 0;
+        const int hi_x = sh->max_x[s];
+        if (hi_x < 0) continue;
+        any = true;
+        by0[s] = sh->min_y[s];
+        // TMA needs the first byte of a box row on a 16-byte boundary (measured: any other start
+        // faults with "illegal instruction", profiles/microbench/tma_probe.cu)
+        xb0[s] = (sh->min_x[s] * 3) & ~15;
+        nbox[s] = (sh->max_y[s] - by0[s] + kBoxRows) / kBoxRows;
+        // (the funnel-shift gather may read a few bytes past a pixel: the next row, or the tail)
+        if (nbox[s] > a.stage_boxes || hi_x * 3 + 3 - xb0[s] > a.stage_pitch) staged = false;
+    }
+
+    // turn packed coordinates into byte offsets: within the staged rectangle (pixels without a
+    // source point at the zeroed tail), or within the frame (-1 = no source)
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+#pragma unroll
+        for (int p = 0; p < kPxPerThread; ++p) {
+            const int v = loc[s][p];
+            const int sx = v & 0xffff, sy = v >> 16;
+            if (staged)
+                loc[s][p] = (v >= 0) ? (sy - by0[s]) * a.stage_pitch + sx * 3 - xb0[s] : slot_bytes - 128;
+            else
+                loc[s][p] = (v >= 0) ? sy * a.src_pitch + sx * 3 : -1;
+        }
+    }
+
+    unsigned tx_bytes = 0;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) tx_bytes += (unsigned)(nbox[s] * kBoxRows * a.stage_pitch);
+    const bool use_tma = staged && any;
+
+    auto issue_loads = [&](int f) {  // one thread
+        const int b = (a.n_buffers == 2) ? (f & 1) : 0;
+        ptx::mbarrier_arrive_expect_tx(&sh->bar[b], tx_bytes);
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
+            for (int k = 0; k < nbox[s]; ++k)
+                ptx::tma_load_3d(stages + (b * NSLOT + s) * slot_bytes + k * kBoxRows * a.stage_pitch, &a.src_map,
+                                 xb0[s] >> 1, by0[s] + k * kBoxRows, f, &sh->bar[b]);
+    };
+
+    if (use_tma && tid == 0) issue_loads(0);
+
+    // ---------------------------------------------------------------- per frame: 3. stage 4. gather 5. store
+    for (int f = 0; f < a.n_frames; ++f) {
+        const int b = (a.n_buffers == 2) ? (f & 1) : 0;
+        const unsigned char* __restrict__ frame = a.src_px + (long long)f * a.src_frame_stride;
+        unsigned char* out_tile = out_tiles + b * kOutTileBytes;
+        const unsigned char* stage_a = stages + (b * NSLOT) * slot_bytes;
+        const unsigned char* stage_b = stage_a + S1 * slot_bytes;
+
+        if (f > 0) {
+            // out_tile[b] was last stored by frame f - n_buffers, stage[b] last read by the same frame
+            if (tid == 0) {
+                if (a.n_buffers == 2) ptx::bulk_wait_read1();
+                else ptx::bulk_wait_read0();
+            }
+            __syncthreads();
+            if (a.n_buffers == 1 && use_tma && tid == 0) issue_loads(f);
+        }
+        if (a.n_buffers == 2 && use_tma && tid == 0 && f + 1 < a.n_frames) issue_loads(f + 1);
+        if (use_tma) ptx::mbarrier_wait(&sh->bar[b], (unsigned)((a.n_buffers == 2 ? (f >> 1) : f) & 1));
+
+#pragma unroll
+        for (int q = 0; q < kRowsPerThread; ++q) {
+            unsigned px[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int p = q * 4 + k;
+                unsigned v0, v1 = 0;
+                if (staged) {
+                    v0 = pick_px(stage_a, loc[0][p]);
+                    if (DBL) v1 = pick_px(stage_b, loc[S1][p]);
+                } else {
+                    v0 = (loc[0][p] >= 0) ? pick_px_global(frame, loc[0][p]) : 0u;
+                    if (DBL) v1 = (loc[S1][p] >= 0) ? pick_px_global(frame, loc[S1][p]) : 0u;
+                }
+                if (DBL) {
+                    if (WGT_IN_SMEM) {
+                        const double2 w = w_scratch[p * kTileThreads + tid];
+                        px[k] = blend_px(v0, w.x, v1, w.y);
+                    } else {
+                        px[k] = blend_px(v0, wrow[q][0], v1, wrow[q][1]);
+                    }
+                } else {
+                    px[k] = v0;
+                }
+            }
+            unsigned* o = reinterpret_cast<unsigned*>(out_tile + (rg * kRowsPerThread + q) * kOutRowBytes + qc * 12);
+            o[0] = px[0] | (px[1] << 24);
+            o[1] = (px[1] >> 8) | (px[2] << 16);
+            o[2] = (px[2] >> 16) | (px[3] << 8);
+        }
+
+        ptx::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            ptx::tma_store_3d(&a.dst_map, x0 * 3, y0, f, out_tile);
+            ptx::bulk_commit();
+        }
+    }
+    if (tid == 0) ptx::bulk_wait_read0();
+}
+
+template <int SRC_KIND, int MODE>
+inline int tiled_smem_bytes(int stage_pitch, int stage_boxes, int n_buffers) {
+    const int nslot = (SRC_KIND == PB_KIND_DOUBLE) ? 2 : 1;
+    int bytes = n_buffers * kOutTileBytes + n_buffers * nslot * (stage_boxes * kBoxRows * stage_pitch + 128) +
+                (int)sizeof(TileShared);
+    if (MODE == 0) {
+        bytes += nslot * kPxPerThread * kTileThreads * (int)sizeof(int);
+        if (SRC_KIND == PB_KIND_DOUBLE) bytes += kPxPerThread * kTileThreads * (int)sizeof(double2);
+    }
+    return bytes + 128;
+}
+
+}  // namespace pb

@@ -83,6 +83,48 @@ def _remap_desc(rays: RayPlan, src: ImageGeometry, channels: int) -> _native.Rem
     return d
 
 
+# ----------------------------------------------------------------------------- plans
+
+
+class _PlanCache:
+    """pb_plan handles keyed by (device, descriptor bytes): a geometry that is remapped again
+    (a video, a batch of photos from one camera) reuses its separable device tables."""
+
+    def __init__(self, capacity: int = 32):
+        self._capacity = capacity
+        self._plans = {}  # key -> handle (insertion order = LRU order)
+
+    def get(self, lib, desc: _native.RemapDesc, device_index: int, torch) -> ctypes.c_void_p:
+        key = (device_index, bytes(desc))
+        handle = self._plans.pop(key, None)
+        if handle is None:
+            handle = ctypes.c_void_p()
+            stream = torch.cuda.current_stream()
+            _native.check(lib.pb_plan_create(ctypes.byref(desc), ctypes.c_void_p(stream.cuda_stream),
+                                             ctypes.byref(handle)))
+            stream.synchronize()  # once per geometry: the tables may be used from any stream later
+            while len(self._plans) >= self._capacity:
+                oldest = next(iter(self._plans))
+                lib.pb_plan_destroy(self._plans.pop(oldest))
+        self._plans[key] = handle  # most recently used goes last
+        return handle
+
+    def clear(self):
+        if self._plans:
+            lib = _native.load()
+            for handle in self._plans.values():
+                lib.pb_plan_destroy(handle)
+            self._plans.clear()
+
+
+_plans = _PlanCache()
+
+
+def clear_plan_cache() -> None:
+    """Destroy every cached pb_plan (frees their device tables)."""
+    _plans.clear()
+
+
 # ----------------------------------------------------------------------------- image plumbing
 
 
@@ -162,11 +204,13 @@ def remap_device(rays: RayPlan, src: ImageGeometry, src_dev, out_dev=None):
         raise ValueError(f"out must be a contiguous uint8 tensor of shape {out_shape}")
     desc = _remap_desc(rays, src, c)
     with torch.cuda.device(src_dev.device):
-        _native.check(lib.pb_remap_u8(
-            ctypes.byref(desc),
+        plan = _plans.get(lib, desc, src_dev.device.index or 0, torch)
+        stream = _stream_ptr(torch)
+        _native.check(lib.pb_plan_remap_u8(
+            plan,
             ctypes.c_void_p(src_dev.data_ptr()), ctypes.c_int64(h * w * c),
             ctypes.c_void_p(out_dev.data_ptr()), ctypes.c_int64(oh * ow * c),
-            ctypes.c_int32(frames), _stream_ptr(torch)))
+            ctypes.c_int32(frames), stream))
     return out_dev
 
 
