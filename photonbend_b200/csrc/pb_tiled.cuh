@@ -101,10 +101,13 @@ struct TileShared {
     int min_x[2], max_x[2], min_y[2], max_y[2];
 };
 
+constexpr int kNoLin = 0x40000000;  // "no source pixel" while offsets are still relative to (0, 0)
+
 __device__ __forceinline__ unsigned pick_px(const unsigned char* __restrict__ stage, int b) {
-    // 3 bytes at byte offset b of the staged rectangle: two aligned words + funnel shift
+    // the 3 bytes at byte offset b of the staged rectangle (+ one byte of garbage on top): two
+    // aligned words and a funnel shift; SHF takes its shift count modulo 32, so b * 8 does
     const unsigned* w = reinterpret_cast<const unsigned*>(stage + (b & ~3));
-    return __funnelshift_r(w[0], w[1], (b & 3) * 8) & 0x00ffffffu;
+    return __funnelshift_r(w[0], w[1], b << 3);
 }
 
 __device__ __forceinline__ unsigned pick_px_global(const unsigned char* __restrict__ img, int b) {
@@ -112,7 +115,7 @@ __device__ __forceinline__ unsigned pick_px_global(const unsigned char* __restri
 }
 
 __device__ __forceinline__ unsigned blend_px(unsigned a, double wa, unsigned b, double wb) {
-    if (wa == 1.0 && wb == 1.0) return __vadd4(a, b) & 0x00ffffffu;  // exact: bytes add mod 256
+    if (wa == 1.0 && wb == 1.0) return __vadd4(a, b);  // exact: bytes add mod 256 (top byte is garbage anyway)
     unsigned r = 0;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -120,16 +123,103 @@ __device__ __forceinline__ unsigned blend_px(unsigned a, double wa, unsigned b, 
     return r;
 }
 
+// 4 pixels (low 3 bytes of each word) -> 12 packed bytes
+__device__ __forceinline__ void store_quad(unsigned* o, const unsigned px[4]) {
+    o[0] = __byte_perm(px[0], px[1], 0x4210);
+    o[1] = __byte_perm(px[1], px[2], 0x5421);
+    o[2] = __byte_perm(px[2], px[3], 0x6542);
+}
+
 // projection.py:223-231 + 254-259 for both coordinates of one camera sample, the way the tiled
-// kernel wants it: "0 <= trunc(v) < n" is "-1 < v < n" on the reals (NaN fails every compare).
-__device__ __forceinline__ int camera_xy_fast(double c, double s, double dist, int h, int w, double cy, double cx,
-                                              int col0, bool flip) {
+// kernel wants it: "0 <= trunc(v) < n" is "-1 < v < n" on the reals (NaN fails every compare),
+// and trunc(|v|) sits in the low word of |v| + 2^52 rounded toward zero.
+__device__ __forceinline__ bool camera_px(double c, double s, double dist, int h, int w, double cy, double cx,
+                                          int& px, int& py) {
     const double fx = __dadd_rn(__dmul_rn(c, dist), cx);
-    const double fy = __dadd_rn(__dmul_rn(__dmul_rn(s, dist), -1.0), cy);
-    const bool ok = fx > -1.0 && fx < (double)w && fy > -1.0 && fy < (double)h;
-    const int px = __double2loint(__dadd_rz(fabs(fx), 4503599627370496.0));
-    const int py = __double2loint(__dadd_rz(fabs(fy), 4503599627370496.0));
-    return ok ? ((py << 16) | (col0 + (flip ? (w - 1 - px) : px))) : kNoPixel;
+    const double fy = __dadd_rn(-__dmul_rn(s, dist), cy);  // (im * -1) + cy: negation is exact
+    px = __double2loint(__dadd_rz(fabs(fx), 4503599627370496.0));
+    py = __double2loint(__dadd_rz(fabs(fy), 4503599627370496.0));
+    return fx > -1.0 && fx < (double)w && fy > -1.0 && fy < (double)h;
+}
+
+struct Footprint {
+    int mnx, mny, mxx, mxy;
+    __device__ __forceinline__ void reset() {
+        mnx = mny = 0x7fffffff;
+        mxx = mxy = -1;
+    }
+    __device__ __forceinline__ void add(int x, int y) {
+        mnx = min(mnx, x);
+        mxx = max(mxx, x);
+        mny = min(mny, y);
+        mxy = max(mxy, y);
+    }
+};
+
+// Slow path of a tile whose footprint cannot be staged (it holds a pole of the source, straddles
+// the +-pi seam of a panorama, or is simply too wide): every pixel is resolved again and read
+// straight from global memory.  Rare by construction; clarity over speed.
+template <int OUT_KIND, int SRC_KIND, int MODE>
+__device__ __noinline__ void direct_tile(const TiledArgs& a, const int* xy_scratch, const double2* w_scratch,
+                                         unsigned char* out_tile, int x0, int y0) {
+    constexpr bool DBL = (SRC_KIND == PB_KIND_DOUBLE);
+    const int tid = threadIdx.x;
+    for (int f = 0; f < a.n_frames; ++f) {
+        const unsigned char* __restrict__ frame = a.src_px + (long long)f * a.src_frame_stride;
+        if (f > 0) {
+            if (tid == 0) ptx::bulk_wait_read0();
+            __syncthreads();
+        }
+        for (int e = tid; e < kTileW * kTileH; e += kTileThreads) {
+            const int r = e / kTileW, c = e - r * kTileW;
+            const int i = min(y0 + r, a.out.H - 1), j = min(x0 + c, a.out.W - 1);
+            Lookup L;
+            if (MODE == 1) {
+                // separable tables hold exactly what source_lookup would recompute for this pixel
+                const double2 cs = __ldg(reinterpret_cast<const double2*>(a.col_tab) + j);
+                const double2 r01 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i);
+                const double2 r23 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i + 1);
+                L.xy1 = kNoPixel;
+                L.w0 = r23.x;
+                L.w1 = r23.y;
+                if (DBL) {
+                    L.xy0 = camera_xy_from(cs.x, cs.y, r01.x, a.src.H, a.src.wl, a.src.cy, a.src.cxl, 0, false);
+                    L.xy1 = camera_xy_from(cs.x, cs.y, r01.y, a.src.H, a.src.wr, a.src.cy, a.src.cxr, a.src.wl, true);
+                } else {
+                    L.xy0 = camera_xy_from(cs.x, cs.y, r01.x, a.src.H, a.src.W, a.src.cy, a.src.cx, 0, false);
+                }
+            } else {
+                // generic rays were parked in shared memory by the resolve step: pixel e belongs to
+                // thread (r % 32) * 8 + c / 4, slot (r / 32) * 4 + c % 4
+                const int t = (r & (kRowGroups - 1)) * kQuadsPerRow + (c >> 2);
+                const int p = (r / kRowGroups) * 4 + (c & 3);
+                L.xy0 = xy_scratch[p * kTileThreads + t];
+                L.xy1 = kNoPixel;
+                L.w0 = L.w1 = 1.0;
+                if (DBL) {
+                    L.xy1 = xy_scratch[(kPxPerThread + p) * kTileThreads + t];
+                    const double2 w = w_scratch[p * kTileThreads + t];
+                    L.w0 = w.x;
+                    L.w1 = w.y;
+                }
+            }
+            unsigned v0 = 0, v1 = 0;
+            if (L.xy0 >= 0) v0 = pick_px_global(frame, (L.xy0 >> 16) * a.src_pitch + (L.xy0 & 0xffff) * 3);
+            if (DBL && L.xy1 >= 0) v1 = pick_px_global(frame, (L.xy1 >> 16) * a.src_pitch + (L.xy1 & 0xffff) * 3);
+            const unsigned v = DBL ? blend_px(v0, L.w0, v1, L.w1) : v0;
+            unsigned char* o = out_tile + r * kOutRowBytes + c * 3;
+            o[0] = (unsigned char)v;
+            o[1] = (unsigned char)(v >> 8);
+            o[2] = (unsigned char)(v >> 16);
+        }
+        ptx::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            ptx::tma_store_3d(&a.dst_map, x0 * 3, y0, f, out_tile);
+            ptx::bulk_commit();
+        }
+    }
+    if (tid == 0) ptx::bulk_wait_read0();
 }
 
 // MODE: 0 = generic per-pixel rays (any output, any rotations), 1 = separable tables
@@ -150,6 +240,9 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     int* xy_scratch = reinterpret_cast<int*>(sh + 1);                        // MODE 0: [NSLOT][8][256]
     double2* w_scratch = reinterpret_cast<double2*>(xy_scratch + NSLOT * kPxPerThread * kTileThreads);  // [8][256]
 
+    // thread -> pixels: quad column qc (4 consecutive pixels), rows rg and rg + 32.  A warp then
+    // covers 32 columns x 4 consecutive rows, which makes its 12-byte quad stores into the
+    // 96-byte-pitch output tile hit 32 distinct banks.
     const int tid = threadIdx.x;
     const int qc = tid & (kQuadsPerRow - 1);
     const int rg = tid >> 3;
@@ -177,14 +270,13 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     __syncthreads();
 
     // ---------------------------------------------------------------- 1. resolve  2. footprint
+    // loc = sy * stage_pitch + sx * 3 for now (kNoLin: no source pixel); made relative to the staged
+    // rectangle once the footprint is known
     int loc[NSLOT][kPxPerThread];
     double wrow[kRowsPerThread][2];  // separable double source: blend weights per row
-    int mnx[NSLOT], mny[NSLOT], mxx[NSLOT], mxy[NSLOT];
+    Footprint fp[NSLOT];
 #pragma unroll
-    for (int s = 0; s < NSLOT; ++s) {
-        mnx[s] = mny[s] = 0x7fffffff;
-        mxx[s] = mxy[s] = -1;
-    }
+    for (int s = 0; s < NSLOT; ++s) fp[s].reset();
 
     if (MODE == 1) {
         double2 cs[4];
@@ -193,7 +285,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 #pragma unroll
         for (int q = 0; q < kRowsPerThread; ++q) {
             // rows past the image edge repeat the last row: they widen nothing and TMA clips them
-            const int i = min(y0 + rg * kRowsPerThread + q, a.out.H - 1);
+            const int i = min(y0 + rg + q * kRowGroups, a.out.H - 1);
             const double2 r01 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i);
             if (DBL) {
                 const double2 r23 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i + 1);
@@ -202,11 +294,19 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+                int px, py;
                 if (DBL) {
-                    loc[0][q * 4 + k] = camera_xy_fast(cs[k].x, cs[k].y, r01.x, a.src.H, a.src.wl, a.src.cy, a.src.cxl, 0, false);
-                    loc[S1][q * 4 + k] = camera_xy_fast(cs[k].x, cs[k].y, r01.y, a.src.H, a.src.wr, a.src.cy, a.src.cxr, a.src.wl, true);
+                    const bool okl = camera_px(cs[k].x, cs[k].y, r01.x, a.src.H, a.src.wl, a.src.cy, a.src.cxl, px, py);
+                    if (okl) fp[0].add(px, py);
+                    loc[0][q * 4 + k] = okl ? py * a.stage_pitch + px * 3 : kNoLin;
+                    const bool okr = camera_px(cs[k].x, cs[k].y, r01.y, a.src.H, a.src.wr, a.src.cy, a.src.cxr, px, py);
+                    px = a.src.W - 1 - px;  // right half, mirrored: wl + (wr - 1 - px)
+                    if (okr) fp[S1].add(px, py);
+                    loc[S1][q * 4 + k] = okr ? py * a.stage_pitch + px * 3 : kNoLin;
                 } else {
-                    loc[0][q * 4 + k] = camera_xy_fast(cs[k].x, cs[k].y, r01.x, a.src.H, a.src.W, a.src.cy, a.src.cx, 0, false);
+                    const bool ok = camera_px(cs[k].x, cs[k].y, r01.x, a.src.H, a.src.W, a.src.cy, a.src.cx, px, py);
+                    if (ok) fp[0].add(px, py);
+                    loc[0][q * 4 + k] = ok ? py * a.stage_pitch + px * 3 : kNoLin;
                 }
             }
         }
@@ -214,7 +314,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         // generic rays: heavy float64 code, kept rolled (results parked in shared memory)
 #pragma unroll 1
         for (int p = 0; p < kPxPerThread; ++p) {
-            const int i = min(y0 + rg * kRowsPerThread + (p >> 2), a.out.H - 1);
+            const int i = min(y0 + rg + (p >> 2) * kRowGroups, a.out.H - 1);
             const int j = min(jx + (p & 3), a.out.W - 1);
             Ray r = output_ray<OUT_KIND>(a.out, i, j);
             for (int n = 0; n < a.rot.n; ++n) r = rotate_ray(r, a.rot.m[n]);
@@ -226,34 +326,28 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             }
         }
 #pragma unroll
-        for (int p = 0; p < kPxPerThread; ++p) {
-            loc[0][p] = xy_scratch[p * kTileThreads + tid];
-            if (DBL) loc[S1][p] = xy_scratch[(kPxPerThread + p) * kTileThreads + tid];
+        for (int s = 0; s < NSLOT; ++s) {
+#pragma unroll
+            for (int p = 0; p < kPxPerThread; ++p) {
+                const int v = xy_scratch[(s * kPxPerThread + p) * kTileThreads + tid];
+                const int sx = v & 0xffff, sy = v >> 16;
+                if (v >= 0) fp[s].add(sx, sy);
+                loc[s][p] = (v >= 0) ? sy * a.stage_pitch + sx * 3 : kNoLin;
+            }
         }
     }
 
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
-#pragma unroll
-        for (int p = 0; p < kPxPerThread; ++p) {
-            const int v = loc[s][p];
-            if (v >= 0) {
-                const int sx = v & 0xffff, sy = v >> 16;
-                mnx[s] = min(mnx[s], sx);
-                mxx[s] = max(mxx[s], sx);
-                mny[s] = min(mny[s], sy);
-                mxy[s] = max(mxy[s], sy);
-            }
-        }
-        mnx[s] = __reduce_min_sync(0xffffffffu, mnx[s]);
-        mny[s] = __reduce_min_sync(0xffffffffu, mny[s]);
-        mxx[s] = __reduce_max_sync(0xffffffffu, mxx[s]);
-        mxy[s] = __reduce_max_sync(0xffffffffu, mxy[s]);
-        if ((tid & 31) == 0 && mxx[s] >= 0) {
-            atomicMin(&sh->min_x[s], mnx[s]);
-            atomicMin(&sh->min_y[s], mny[s]);
-            atomicMax(&sh->max_x[s], mxx[s]);
-            atomicMax(&sh->max_y[s], mxy[s]);
+        const int mnx = __reduce_min_sync(0xffffffffu, fp[s].mnx);
+        const int mny = __reduce_min_sync(0xffffffffu, fp[s].mny);
+        const int mxx = __reduce_max_sync(0xffffffffu, fp[s].mxx);
+        const int mxy = __reduce_max_sync(0xffffffffu, fp[s].mxy);
+        if ((tid & 31) == 0 && mxx >= 0) {
+            atomicMin(&sh->min_x[s], mnx);
+            atomicMin(&sh->min_y[s], mny);
+            atomicMax(&sh->max_x[s], mxx);
+            atomicMax(&sh->max_y[s], mxy);
         }
     }
     __syncthreads();
@@ -275,26 +369,24 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         // (the funnel-shift gather may read a few bytes past a pixel: the next row, or the tail)
         if (nbox[s] > a.stage_boxes || hi_x * 3 + 3 - xb0[s] > a.stage_pitch) staged = false;
     }
+    if (!staged) {  // block-uniform
+        direct_tile<OUT_KIND, SRC_KIND, MODE>(a, xy_scratch, w_scratch, out_tiles, x0, y0);
+        return;
+    }
 
-    // turn packed coordinates into byte offsets: within the staged rectangle (pixels without a
-    // source point at the zeroed tail), or within the frame (-1 = no source)
+    // offsets relative to the staged rectangle; pixels without a source land on the zeroed tail
+    // (an unsigned min: kNoLin plus any rectangle origin stays huge)
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
+        const int origin = by0[s] * a.stage_pitch + xb0[s];
 #pragma unroll
-        for (int p = 0; p < kPxPerThread; ++p) {
-            const int v = loc[s][p];
-            const int sx = v & 0xffff, sy = v >> 16;
-            if (staged)
-                loc[s][p] = (v >= 0) ? (sy - by0[s]) * a.stage_pitch + sx * 3 - xb0[s] : slot_bytes - 128;
-            else
-                loc[s][p] = (v >= 0) ? sy * a.src_pitch + sx * 3 : -1;
-        }
+        for (int p = 0; p < kPxPerThread; ++p)
+            loc[s][p] = (int)min((unsigned)(loc[s][p] - origin), (unsigned)(slot_bytes - 128));
     }
 
     unsigned tx_bytes = 0;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) tx_bytes += (unsigned)(nbox[s] * kBoxRows * a.stage_pitch);
-    const bool use_tma = staged && any;
 
     auto issue_loads = [&](int f) {  // one thread
         const int b = (a.n_buffers == 2) ? (f & 1) : 0;
@@ -306,12 +398,11 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                                  xb0[s] >> 1, by0[s] + k * kBoxRows, f, &sh->bar[b]);
     };
 
-    if (use_tma && tid == 0) issue_loads(0);
+    if (any && tid == 0) issue_loads(0);
 
     // ---------------------------------------------------------------- per frame: 3. stage 4. gather 5. store
     for (int f = 0; f < a.n_frames; ++f) {
         const int b = (a.n_buffers == 2) ? (f & 1) : 0;
-        const unsigned char* __restrict__ frame = a.src_px + (long long)f * a.src_frame_stride;
         unsigned char* out_tile = out_tiles + b * kOutTileBytes;
         const unsigned char* stage_a = stages + (b * NSLOT) * slot_bytes;
         const unsigned char* stage_b = stage_a + S1 * slot_bytes;
@@ -323,10 +414,10 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                 else ptx::bulk_wait_read0();
             }
             __syncthreads();
-            if (a.n_buffers == 1 && use_tma && tid == 0) issue_loads(f);
+            if (a.n_buffers == 1 && any && tid == 0) issue_loads(f);
         }
-        if (a.n_buffers == 2 && use_tma && tid == 0 && f + 1 < a.n_frames) issue_loads(f + 1);
-        if (use_tma) ptx::mbarrier_wait(&sh->bar[b], (unsigned)((a.n_buffers == 2 ? (f >> 1) : f) & 1));
+        if (a.n_buffers == 2 && any && tid == 0 && f + 1 < a.n_frames) issue_loads(f + 1);
+        if (any) ptx::mbarrier_wait(&sh->bar[b], (unsigned)((a.n_buffers == 2 ? (f >> 1) : f) & 1));
 
 #pragma unroll
         for (int q = 0; q < kRowsPerThread; ++q) {
@@ -334,15 +425,9 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int p = q * 4 + k;
-                unsigned v0, v1 = 0;
-                if (staged) {
-                    v0 = pick_px(stage_a, loc[0][p]);
-                    if (DBL) v1 = pick_px(stage_b, loc[S1][p]);
-                } else {
-                    v0 = (loc[0][p] >= 0) ? pick_px_global(frame, loc[0][p]) : 0u;
-                    if (DBL) v1 = (loc[S1][p] >= 0) ? pick_px_global(frame, loc[S1][p]) : 0u;
-                }
+                const unsigned v0 = pick_px(stage_a, loc[0][p]);
                 if (DBL) {
+                    const unsigned v1 = pick_px(stage_b, loc[S1][p]);
                     if (WGT_IN_SMEM) {
                         const double2 w = w_scratch[p * kTileThreads + tid];
                         px[k] = blend_px(v0, w.x, v1, w.y);
@@ -353,10 +438,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                     px[k] = v0;
                 }
             }
-            unsigned* o = reinterpret_cast<unsigned*>(out_tile + (rg * kRowsPerThread + q) * kOutRowBytes + qc * 12);
-            o[0] = px[0] | (px[1] << 24);
-            o[1] = (px[1] >> 8) | (px[2] << 16);
-            o[2] = (px[2] >> 16) | (px[3] << 8);
+            store_quad(reinterpret_cast<unsigned*>(out_tile + (rg + q * kRowGroups) * kOutRowBytes + qc * 12), px);
         }
 
         ptx::fence_async_smem();
