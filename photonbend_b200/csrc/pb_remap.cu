@@ -346,7 +346,7 @@ constexpr int kMaxTiledSmem = 200 * 1024;
 
 template <int OUT_KIND, int SRC_KIND, int MODE>
 static cudaError_t launch_tiled_one(const TiledArgs& a, cudaStream_t st) {
-    const int smem = tiled_smem_bytes<SRC_KIND, MODE>(a.stage_pitch, a.stage_boxes, a.n_buffers);
+    const int smem = tiled_smem_bytes<SRC_KIND, MODE>(a.stage_pitch, a.stage_boxes, a.n_buffers, a.n_out);
     static bool configured = false;  // per instantiation; the attribute is per device function
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE>,
@@ -428,6 +428,63 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     p.device = -1;
 }
 
+// Footprint census of a geometry (one probe launch of the tiled kernel, nothing is remapped):
+// picks the smallest staged-row width and box count that hold the footprint of ~all tiles, so that
+// the stage buffers are as small -- and the occupancy as high -- as this geometry allows.
+static void tune_stage(pb_plan& p, cudaStream_t st) {
+    if (p.desc.channels != 3) return;
+    int* census = nullptr;
+    const int n = kProbePitchBins + kProbeBoxBins;
+    if (cudaMalloc((void**)&census, n * sizeof(int)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;
+    }
+    cudaMemsetAsync(census, 0, n * sizeof(int), st);
+    TiledArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.out = p.out;
+    a.src = p.src;
+    a.rot = p.rot;
+    a.col_tab = p.tables;
+    a.row_tab = p.tables ? p.tables + 2 * (size_t)p.out.W : nullptr;
+    a.n_frames = 0;
+    a.src_pitch = p.src.W * 3;
+    a.stage_pitch = 512;
+    a.stage_boxes = 1;
+    a.n_buffers = 1;
+    a.n_out = 1;
+    a.probe = census;
+    int h[kProbePitchBins + kProbeBoxBins];
+    if (launch_tiled(a, p.separable && p.tables != nullptr, st) == cudaSuccess &&
+        cudaMemcpyAsync(h, census, sizeof(h), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+        cudaStreamSynchronize(st) == cudaSuccess) {
+        long long tiles = 0;
+        for (int k = 0; k < kProbePitchBins; ++k) tiles += h[k];
+        if (tiles > 0) {
+            const long long need = tiles - tiles / 200;  // all but 0.5 % of the tiles
+            long long acc = 0;
+            int pitch_bin = kProbePitchBins - 1, box_bin = kProbeBoxBins - 1;
+            for (int k = 0; k < kProbePitchBins; ++k) {
+                acc += h[k];
+                if (acc >= need) { pitch_bin = k; break; }
+            }
+            acc = 0;
+            for (int k = 0; k < kProbeBoxBins; ++k) {
+                acc += h[kProbePitchBins + k];
+                if (acc >= need) { box_bin = k; break; }
+            }
+            int pitch = 16 * (pitch_bin < 4 ? 4 : pitch_bin), boxes = box_bin < 1 ? 1 : box_bin;
+            if (pitch > 512) pitch = 512;             // u16 tensor map: at most 256 elements per box row
+            while (boxes > 1 && boxes * kBoxRows * pitch > 48 * 1024) --boxes;
+            p.stage_pitch = pitch;
+            p.stage_boxes = boxes;
+        }
+    } else {
+        (void)cudaGetLastError();
+    }
+    cudaFree(census);
+}
+
 static size_t table_doubles(const pb_plan& p) { return 2 * (size_t)p.out.W + 4 * (size_t)p.out.H; }
 
 static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st) {
@@ -461,7 +518,19 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         const bool dbl = p.src.kind == PB_KIND_DOUBLE;
         a.stage_pitch = p.stage_pitch;
         a.stage_boxes = p.stage_boxes;
-        a.n_buffers = (multi && !dbl) ? 2 : 1;
+        // a second stage buffer lets the loads of the next (frame, slot) item overlap the current
+        // gather; taken when three CTAs per SM still fit
+        a.n_out = multi ? 2 : 1;
+        a.n_buffers = 1;
+        if (multi || dbl) {
+            const int mode = (p.separable && tables != nullptr) ? 1 : 0;
+            int two;
+            if (dbl) two = mode ? tiled_smem_bytes<PB_KIND_DOUBLE, 1>(a.stage_pitch, a.stage_boxes, 2, a.n_out)
+                                : tiled_smem_bytes<PB_KIND_DOUBLE, 0>(a.stage_pitch, a.stage_boxes, 2, a.n_out);
+            else two = mode ? tiled_smem_bytes<PB_KIND_CAMERA, 1>(a.stage_pitch, a.stage_boxes, 2, a.n_out)
+                            : tiled_smem_bytes<PB_KIND_CAMERA, 0>(a.stage_pitch, a.stage_boxes, 2, a.n_out);
+            if (two <= 75 * 1024) a.n_buffers = 2;
+        }
         if (encode_frames_map(&a.src_map, src, src_pitch, p.src.H, n_frames, src_frame_stride, 2, a.stage_pitch,
                               kBoxRows) &&
             encode_frames_map(&a.dst_map, dst, dst_pitch, p.out.H, n_frames, dst_frame_stride, 1, kOutRowBytes,
@@ -550,6 +619,7 @@ int pb_plan_create(const pb_remap_desc* desc, void* stream, pb_plan** plan_out) 
             return cuda_fail(e, "pb_plan_create tables");
         }
     }
+    tune_stage(*p, (cudaStream_t)stream);
     *plan_out = p;
     return PB_OK;
 }

@@ -9,14 +9,17 @@
 //                an un-rotated equirectangular output, from the separable tables (cos/sin of the
 //                column's longitude, lens radius of the row's latitude) that pb_tables_kernel wrote
 //                once per geometry.  No coordinate map ever exists in memory.
-//   2. footprint the CTA reduces the bounding rectangle of the source pixels its tile reads
-//                (warp redux + shared atomics), one rectangle per source "slot" (a double-fisheye
-//                source has two: left and right lens).
-//   3. stage     for every frame of the batch one elected thread pulls the rectangle into shared
+//   2. footprint the bounding rectangle of the source pixels the tile reads, one per source "slot"
+//                (a double-fisheye source has two: left and right lens).  Separable geometry: one
+//                warp per slot derives it from the tile's 32 columns x {smallest, largest} lens
+//                radius of its rows (the coordinates are monotone in the radius), and learns
+//                whether every pixel of the tile is inside the source (then the per-pixel bounds
+//                tests are skipped).  Generic rays: warp redux + shared atomics over all pixels.
+//   3. stage     for every (frame, slot) item one elected thread pulls the rectangle into shared
 //                memory with TMA tensor-map box loads (cp.async.bulk.tensor, 16-row boxes, one
 //                mbarrier per stage buffer; the hardware zero-fills what hangs over the image
-//                border).  With several frames per launch the loads of frame f+1 are in flight
-//                while frame f is gathered (two stage buffers).  Tiles whose footprint does not
+//                border).  Items rotate through two stage buffers, so the loads of the next item
+//                are in flight while the current one is gathered.  Tiles whose footprint does not
 //                fit (a pole, the +-pi seam of a panorama) gather straight from global memory.
 //   4. gather    threads pick their pixels out of shared memory (two aligned 32-bit loads + a
 //                funnel shift per pixel), blend the two slots where the source is a double
@@ -59,9 +62,16 @@ struct TiledArgs {
     int n_frames;
     int src_pitch;    // bytes per source row
     int stage_pitch;  // bytes per staged row (= box width), multiple of 16
-    int stage_boxes;  // capacity of one stage buffer of one slot, in 16-row boxes
-    int n_buffers;    // 1, or 2 when frames are pipelined
+    int stage_boxes;  // capacity of one stage buffer, in 16-row boxes
+    int n_buffers;    // stage buffers: 1, or 2 (loads of the next item overlap the current gather)
+    int n_out;        // output tile buffers: 1, or 2 (the store of frame f overlaps frame f+1)
+    int* probe;       // non-null: footprint census only (see pb_plan_create), nothing is remapped
 };
+
+// footprint census written by a probe launch: how many tiles need a staged row of k*16 bytes
+// (k = 1..32, 0 = tile reads nothing, 33 = more) and how many 16-row boxes (0..16, 17 = more)
+constexpr int kProbePitchBins = 34;
+constexpr int kProbeBoxBins = 18;
 
 // Separable tables for an un-rotated equirect output (a1) feeding a camera (a9) or double (a10)
 // source: everything that depends on the column only, or on the row only, evaluated with exactly
@@ -96,12 +106,11 @@ __global__ void __launch_bounds__(256) pb_tables_kernel(const __grid_constant__ 
     }
 }
 
-struct TileShared {
+struct alignas(16) TileShared {
     uint64_t bar[2];  // one mbarrier per stage buffer
     int min_x[2], max_x[2], min_y[2], max_y[2];
+    int all_valid[2];
 };
-
-constexpr int kNoLin = 0x40000000;  // "no source pixel" while offsets are still relative to (0, 0)
 
 __device__ __forceinline__ unsigned pick_px(const unsigned char* __restrict__ stage, int b) {
     // the 3 bytes at byte offset b of the staged rectangle (+ one byte of garbage on top): two
@@ -130,15 +139,20 @@ __device__ __forceinline__ void store_quad(unsigned* o, const unsigned px[4]) {
     o[2] = __byte_perm(px[2], px[3], 0x6542);
 }
 
-// projection.py:223-231 + 254-259 for both coordinates of one camera sample, the way the tiled
-// kernel wants it: "0 <= trunc(v) < n" is "-1 < v < n" on the reals (NaN fails every compare),
-// and trunc(|v|) sits in the low word of |v| + 2^52 rounded toward zero.
-__device__ __forceinline__ bool camera_px(double c, double s, double dist, int h, int w, double cy, double cx,
-                                          int& px, int& py) {
-    const double fx = __dadd_rn(__dmul_rn(c, dist), cx);
-    const double fy = __dadd_rn(-__dmul_rn(s, dist), cy);  // (im * -1) + cy: negation is exact
-    px = __double2loint(__dadd_rz(fabs(fx), 4503599627370496.0));
-    py = __double2loint(__dadd_rz(fabs(fy), 4503599627370496.0));
+// projection.py:254-259: the float64 coordinates of one camera sample
+__device__ __forceinline__ void camera_fxy(double c, double s, double dist, double cy, double cx, double& fx,
+                                           double& fy) {
+    fx = __dadd_rn(__dmul_rn(c, dist), cx);
+    fy = __dadd_rn(-__dmul_rn(s, dist), cy);  // (im * -1) + cy: the negation is exact
+}
+
+// trunc(|v|) sits in the low word of |v| + 2^52 rounded toward zero (for |v| < 2^32)
+__device__ __forceinline__ int trunc_abs(double v) {
+    return __double2loint(__dadd_rz(fabs(v), 4503599627370496.0));
+}
+
+// projection.py:223-231: "0 <= trunc(v) < n" is "-1 < v < n" on the reals (NaN fails every compare)
+__device__ __forceinline__ bool inside_image(double fx, double fy, int w, int h) {
     return fx > -1.0 && fx < (double)w && fy > -1.0 && fy < (double)h;
 }
 
@@ -154,7 +168,63 @@ struct Footprint {
         mny = min(mny, y);
         mxy = max(mxy, y);
     }
+    __device__ __forceinline__ void warp_reduce() {
+        mnx = __reduce_min_sync(0xffffffffu, mnx);
+        mny = __reduce_min_sync(0xffffffffu, mny);
+        mxx = __reduce_max_sync(0xffffffffu, mxx);
+        mxy = __reduce_max_sync(0xffffffffu, mxy);
+    }
 };
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Footprint of one slot of a separable tile, by ONE warp (lane = row pair, then lane = column):
+// the source coordinates are monotone in the row's lens radius, so the 32 columns evaluated at
+// the smallest and largest radius of the tile's rows bound every pixel of the tile exactly.
+__device__ __forceinline__ void separable_footprint(const TiledArgs& a, int slot, int x0, int y0, int lane,
+                                                    Footprint& fp, bool& all_valid) {
+    const bool dbl = a.src.kind == PB_KIND_DOUBLE;
+    const int w = dbl ? (slot ? a.src.wr : a.src.wl) : a.src.W;
+    const double cx = dbl ? (slot ? a.src.cxr : a.src.cxl) : a.src.cx;
+    // radius range over the 64 rows (NaN radii -- outside a rectilinear lens -- never land anywhere)
+    const int ia = min(y0 + lane, a.out.H - 1), ib = min(y0 + lane + 32, a.out.H - 1);
+    const double da = __ldg(a.row_tab + 4 * ia + slot), db = __ldg(a.row_tab + 4 * ib + slot);
+    const double d_lo = warp_min(fmin(da, db)), d_hi = warp_max(fmax(da, db));
+    const int any_nan = __any_sync(0xffffffffu, (da != da) || (db != db));
+    // this lane's column at both radii
+    const double2 cs = __ldg(reinterpret_cast<const double2*>(a.col_tab) + min(x0 + lane, a.out.W - 1));
+    double fxa, fya, fxb, fyb;
+    camera_fxy(cs.x, cs.y, d_lo, a.src.cy, cx, fxa, fya);
+    camera_fxy(cs.x, cs.y, d_hi, a.src.cy, cx, fxb, fyb);
+    const double xlo = fmin(fxa, fxb), xhi = fmax(fxa, fxb), ylo = fmin(fya, fyb), yhi = fmax(fya, fyb);
+    const bool hit = xlo < (double)w && xhi > -1.0 && ylo < (double)a.src.H && yhi > -1.0;
+    const bool inside = xlo > -1.0 && xhi < (double)w && ylo > -1.0 && yhi < (double)a.src.H;
+    fp.reset();
+    if (hit) {
+        int ixlo = (xlo <= 0.0) ? 0 : __double2int_rz(xlo);
+        int ixhi = (xhi >= (double)(w - 1)) ? w - 1 : __double2int_rz(xhi);
+        const int iylo = (ylo <= 0.0) ? 0 : __double2int_rz(ylo);
+        const int iyhi = (yhi >= (double)(a.src.H - 1)) ? a.src.H - 1 : __double2int_rz(yhi);
+        if (slot) {  // right half of a double image, mirrored: column wl + (wr - 1 - px)
+            const int t = a.src.W - 1 - ixhi;
+            ixhi = a.src.W - 1 - ixlo;
+            ixlo = t;
+        }
+        fp.add(ixlo, iylo);
+        fp.add(ixhi, iyhi);
+    }
+    fp.warp_reduce();
+    all_valid = __all_sync(0xffffffffu, inside) && !any_nan;
+}
 
 // Slow path of a tile whose footprint cannot be staged (it holds a pole of the source, straddles
 // the +-pi seam of a panorama, or is simply too wide): every pixel is resolved again and read
@@ -232,11 +302,12 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     constexpr bool WGT_IN_SMEM = DBL && MODE == 0;  // per-pixel weights live in shared memory
 
     extern __shared__ __align__(128) unsigned char smem[];
-    // [ out tiles: n_buffers x 6144 ][ stage: n_buffers x NSLOT x (boxes*16*pitch + 128) ][ TileShared ][ scratch ]
-    const int slot_bytes = a.stage_boxes * kBoxRows * a.stage_pitch + 128;  // + zeroed tail
+    // [ out tiles: n_out x 6144 ][ stage buffers: n_buffers x (boxes*16*pitch + 128) ][ TileShared ][ scratch ]
+    const int buf_bytes = a.stage_boxes * kBoxRows * a.stage_pitch + 128;  // + zeroed tail
+    const int ztail = buf_bytes - 128;  // where pixels without a source read their black
     unsigned char* out_tiles = smem;
-    unsigned char* stages = smem + a.n_buffers * kOutTileBytes;
-    TileShared* sh = reinterpret_cast<TileShared*>(stages + a.n_buffers * NSLOT * slot_bytes);
+    unsigned char* stages = smem + a.n_out * kOutTileBytes;
+    TileShared* sh = reinterpret_cast<TileShared*>(stages + a.n_buffers * buf_bytes);
     int* xy_scratch = reinterpret_cast<int*>(sh + 1);                        // MODE 0: [NSLOT][8][256]
     double2* w_scratch = reinterpret_cast<double2*>(xy_scratch + NSLOT * kPxPerThread * kTileThreads);  // [8][256]
 
@@ -251,8 +322,10 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     const int jx = x0 + 4 * qc;
 
     if (tid == 0) {
-        ptx::prefetch_tensormap(&a.src_map);
-        ptx::prefetch_tensormap(&a.dst_map);
+        if (a.probe == nullptr) {
+            ptx::prefetch_tensormap(&a.src_map);
+            ptx::prefetch_tensormap(&a.dst_map);
+        }
         ptx::mbarrier_init(&sh->bar[0], 1);
         ptx::mbarrier_init(&sh->bar[1], 1);
         ptx::fence_mbarrier_init();
@@ -262,56 +335,32 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             sh->min_y[s] = 0x7fffffff;
             sh->max_x[s] = -1;
             sh->max_y[s] = -1;
+            sh->all_valid[s] = 0;
         }
     }
-    // zeroed tail of every stage buffer: where pixels without a source read their black
-    if (tid < a.n_buffers * NSLOT * 8)
-        reinterpret_cast<int4*>(stages + (tid >> 3) * slot_bytes + slot_bytes - 128)[tid & 7] = make_int4(0, 0, 0, 0);
+    if (tid < a.n_buffers * 8)
+        reinterpret_cast<int4*>(stages + (tid >> 3) * buf_bytes + ztail)[tid & 7] = make_int4(0, 0, 0, 0);
     __syncthreads();
 
-    // ---------------------------------------------------------------- 1. resolve  2. footprint
-    // loc = sy * stage_pitch + sx * 3 for now (kNoLin: no source pixel); made relative to the staged
-    // rectangle once the footprint is known
-    int loc[NSLOT][kPxPerThread];
-    double wrow[kRowsPerThread][2];  // separable double source: blend weights per row
-    Footprint fp[NSLOT];
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s) fp[s].reset();
-
+    // ---------------------------------------------------------------- 1. resolve (generic)  2. footprint
     if (MODE == 1) {
-        double2 cs[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) cs[k] = __ldg(reinterpret_cast<const double2*>(a.col_tab) + min(jx + k, a.out.W - 1));
-#pragma unroll
-        for (int q = 0; q < kRowsPerThread; ++q) {
-            // rows past the image edge repeat the last row: they widen nothing and TMA clips them
-            const int i = min(y0 + rg + q * kRowGroups, a.out.H - 1);
-            const double2 r01 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i);
-            if (DBL) {
-                const double2 r23 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i + 1);
-                wrow[q][0] = r23.x;
-                wrow[q][1] = r23.y;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int px, py;
-                if (DBL) {
-                    const bool okl = camera_px(cs[k].x, cs[k].y, r01.x, a.src.H, a.src.wl, a.src.cy, a.src.cxl, px, py);
-                    if (okl) fp[0].add(px, py);
-                    loc[0][q * 4 + k] = okl ? py * a.stage_pitch + px * 3 : kNoLin;
-                    const bool okr = camera_px(cs[k].x, cs[k].y, r01.y, a.src.H, a.src.wr, a.src.cy, a.src.cxr, px, py);
-                    px = a.src.W - 1 - px;  // right half, mirrored: wl + (wr - 1 - px)
-                    if (okr) fp[S1].add(px, py);
-                    loc[S1][q * 4 + k] = okr ? py * a.stage_pitch + px * 3 : kNoLin;
-                } else {
-                    const bool ok = camera_px(cs[k].x, cs[k].y, r01.x, a.src.H, a.src.W, a.src.cy, a.src.cx, px, py);
-                    if (ok) fp[0].add(px, py);
-                    loc[0][q * 4 + k] = ok ? py * a.stage_pitch + px * 3 : kNoLin;
-                }
+        if (tid < 32 * NSLOT) {  // warp s works out the footprint of slot s
+            Footprint fp;
+            bool all_valid;
+            separable_footprint(a, tid >> 5, x0, y0, tid & 31, fp, all_valid);
+            if ((tid & 31) == 0) {
+                sh->min_x[tid >> 5] = fp.mnx;
+                sh->min_y[tid >> 5] = fp.mny;
+                sh->max_x[tid >> 5] = fp.mxx;
+                sh->max_y[tid >> 5] = fp.mxy;
+                sh->all_valid[tid >> 5] = all_valid;
             }
         }
     } else {
         // generic rays: heavy float64 code, kept rolled (results parked in shared memory)
+        Footprint fp[NSLOT];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) fp[s].reset();
 #pragma unroll 1
         for (int p = 0; p < kPxPerThread; ++p) {
             const int i = min(y0 + rg + (p >> 2) * kRowGroups, a.out.H - 1);
@@ -320,47 +369,34 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             for (int n = 0; n < a.rot.n; ++n) r = rotate_ray(r, a.rot.m[n]);
             const Lookup L = source_lookup<SRC_KIND>(a.src, r);
             xy_scratch[p * kTileThreads + tid] = L.xy0;
+            if (L.xy0 >= 0) fp[0].add(L.xy0 & 0xffff, L.xy0 >> 16);
             if (DBL) {
                 xy_scratch[(kPxPerThread + p) * kTileThreads + tid] = L.xy1;
                 w_scratch[p * kTileThreads + tid] = make_double2(L.w0, L.w1);
+                if (L.xy1 >= 0) fp[S1].add(L.xy1 & 0xffff, L.xy1 >> 16);
             }
         }
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
-#pragma unroll
-            for (int p = 0; p < kPxPerThread; ++p) {
-                const int v = xy_scratch[(s * kPxPerThread + p) * kTileThreads + tid];
-                const int sx = v & 0xffff, sy = v >> 16;
-                if (v >= 0) fp[s].add(sx, sy);
-                loc[s][p] = (v >= 0) ? sy * a.stage_pitch + sx * 3 : kNoLin;
+            fp[s].warp_reduce();
+            if ((tid & 31) == 0 && fp[s].mxx >= 0) {
+                atomicMin(&sh->min_x[s], fp[s].mnx);
+                atomicMin(&sh->min_y[s], fp[s].mny);
+                atomicMax(&sh->max_x[s], fp[s].mxx);
+                atomicMax(&sh->max_y[s], fp[s].mxy);
             }
-        }
-    }
-
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s) {
-        const int mnx = __reduce_min_sync(0xffffffffu, fp[s].mnx);
-        const int mny = __reduce_min_sync(0xffffffffu, fp[s].mny);
-        const int mxx = __reduce_max_sync(0xffffffffu, fp[s].mxx);
-        const int mxy = __reduce_max_sync(0xffffffffu, fp[s].mxy);
-        if ((tid & 31) == 0 && mxx >= 0) {
-            atomicMin(&sh->min_x[s], mnx);
-            atomicMin(&sh->min_y[s], mny);
-            atomicMax(&sh->max_x[s], mxx);
-            atomicMax(&sh->max_y[s], mxy);
         }
     }
     __syncthreads();
 
     // rectangle of slot s: rows [by0, by0 + 16*nbox), bytes [xb0, xb0 + stage_pitch) of each row
     int by0[NSLOT], xb0[NSLOT], nbox[NSLOT];
-    bool staged = true, any = false;
+    bool staged = true;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
         by0[s] = xb0[s] = nbox[s] = 0;
         const int hi_x = sh->max_x[s];
         if (hi_x < 0) continue;
-        any = true;
         by0[s] = sh->min_y[s];
         // TMA needs the first byte of a box row on a 16-byte boundary (measured: any other start
         // faults with "illegal instruction", profiles/microbench/tma_probe.cu)
@@ -368,79 +404,155 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         nbox[s] = (sh->max_y[s] - by0[s] + kBoxRows) / kBoxRows;
         // (the funnel-shift gather may read a few bytes past a pixel: the next row, or the tail)
         if (nbox[s] > a.stage_boxes || hi_x * 3 + 3 - xb0[s] > a.stage_pitch) staged = false;
+        if (a.probe != nullptr && tid == 0) {
+            atomicAdd(a.probe + min((hi_x * 3 + 3 - xb0[s] + 15) / 16, kProbePitchBins - 1), 1);
+            atomicAdd(a.probe + kProbePitchBins + min(nbox[s], kProbeBoxBins - 1), 1);
+        }
     }
+    if (a.probe != nullptr) return;
     if (!staged) {  // block-uniform
         direct_tile<OUT_KIND, SRC_KIND, MODE>(a, xy_scratch, w_scratch, out_tiles, x0, y0);
         return;
     }
 
-    // offsets relative to the staged rectangle; pixels without a source land on the zeroed tail
-    // (an unsigned min: kNoLin plus any rectangle origin stays huge)
+    // ---------------------------------------------------------------- 1. resolve (separable) -> byte offsets
+    // loc = byte offset of the pixel inside the staged rectangle of its slot (ztail: no source)
+    int loc[NSLOT][kPxPerThread];
+    double wrow[kRowsPerThread][2];  // separable double source: blend weights per row
+    if (MODE == 1) {
+        double2 cs[4];
 #pragma unroll
-    for (int s = 0; s < NSLOT; ++s) {
-        const int origin = by0[s] * a.stage_pitch + xb0[s];
+        for (int k = 0; k < 4; ++k) cs[k] = __ldg(reinterpret_cast<const double2*>(a.col_tab) + min(jx + k, a.out.W - 1));
+        double2 r01[kRowsPerThread];
 #pragma unroll
-        for (int p = 0; p < kPxPerThread; ++p)
-            loc[s][p] = (int)min((unsigned)(loc[s][p] - origin), (unsigned)(slot_bytes - 128));
+        for (int q = 0; q < kRowsPerThread; ++q) {
+            // rows past the image edge repeat the last row: they widen nothing and TMA clips them
+            const int i = min(y0 + rg + q * kRowGroups, a.out.H - 1);
+            r01[q] = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i);
+            if (DBL) {
+                const double2 r23 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i + 1);
+                wrow[q][0] = r23.x;
+                wrow[q][1] = r23.y;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            const int w = DBL ? (s ? a.src.wr : a.src.wl) : a.src.W;
+            const double cx = DBL ? (s ? a.src.cxr : a.src.cxl) : a.src.cx;
+            const int origin = by0[s] * a.stage_pitch + xb0[s];
+            if (nbox[s] == 0) {  // nothing of this slot is visible from the tile
+#pragma unroll
+                for (int p = 0; p < kPxPerThread; ++p) loc[s][p] = ztail;
+            } else if (sh->all_valid[s]) {  // every pixel lands inside the source: no bounds tests
+#pragma unroll
+                for (int q = 0; q < kRowsPerThread; ++q)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        double fx, fy;
+                        camera_fxy(cs[k].x, cs[k].y, s ? r01[q].y : r01[q].x, a.src.cy, cx, fx, fy);
+                        int px = trunc_abs(fx);
+                        if (s) px = a.src.W - 1 - px;
+                        loc[s][q * 4 + k] = trunc_abs(fy) * a.stage_pitch + (px * 3 - origin);
+                    }
+            } else {
+#pragma unroll
+                for (int q = 0; q < kRowsPerThread; ++q)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        double fx, fy;
+                        camera_fxy(cs[k].x, cs[k].y, s ? r01[q].y : r01[q].x, a.src.cy, cx, fx, fy);
+                        int px = trunc_abs(fx);
+                        if (s) px = a.src.W - 1 - px;
+                        const int off = trunc_abs(fy) * a.stage_pitch + (px * 3 - origin);
+                        loc[s][q * 4 + k] = inside_image(fx, fy, w, a.src.H) ? off : ztail;
+                    }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            const int origin = by0[s] * a.stage_pitch + xb0[s];
+#pragma unroll
+            for (int p = 0; p < kPxPerThread; ++p) {
+                const int v = xy_scratch[(s * kPxPerThread + p) * kTileThreads + tid];
+                loc[s][p] = (v >= 0) ? (v >> 16) * a.stage_pitch + (v & 0xffff) * 3 - origin : ztail;
+            }
+        }
     }
 
-    unsigned tx_bytes = 0;
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s) tx_bytes += (unsigned)(nbox[s] * kBoxRows * a.stage_pitch);
-
-    auto issue_loads = [&](int f) {  // one thread
-        const int b = (a.n_buffers == 2) ? (f & 1) : 0;
-        ptx::mbarrier_arrive_expect_tx(&sh->bar[b], tx_bytes);
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s)
-            for (int k = 0; k < nbox[s]; ++k)
-                ptx::tma_load_3d(stages + (b * NSLOT + s) * slot_bytes + k * kBoxRows * a.stage_pitch, &a.src_map,
-                                 xb0[s] >> 1, by0[s] + k * kBoxRows, f, &sh->bar[b]);
+    // ---------------------------------------------------------------- 3. stage  4. gather  5. store
+    // items = (frame, active slot) pairs, in order; item t uses stage buffer t % n_buffers
+    const int first = (nbox[0] > 0) ? 0 : S1;
+    const int n_act = (nbox[0] > 0) + ((NSLOT == 2 && nbox[S1] > 0) ? 1 : 0);
+    const int n_items = a.n_frames * n_act;
+    auto issue_item = [&](int t) {  // one thread
+        const int b = (a.n_buffers == 2) ? (t & 1) : 0;
+        const int s = (n_act == 2) ? (t & 1) : first;
+        const int f = (n_act == 2) ? (t >> 1) : t;
+        ptx::mbarrier_arrive_expect_tx(&sh->bar[b], (unsigned)(nbox[s] * kBoxRows * a.stage_pitch));
+        for (int k = 0; k < nbox[s]; ++k)
+            ptx::tma_load_3d(stages + b * buf_bytes + k * kBoxRows * a.stage_pitch, &a.src_map, xb0[s] >> 1,
+                             by0[s] + k * kBoxRows, f, &sh->bar[b]);
     };
+    if (tid == 0)
+        for (int t = 0; t < min(a.n_buffers, n_items); ++t) issue_item(t);
 
-    if (any && tid == 0) issue_loads(0);
-
-    // ---------------------------------------------------------------- per frame: 3. stage 4. gather 5. store
+    int t = 0;
     for (int f = 0; f < a.n_frames; ++f) {
-        const int b = (a.n_buffers == 2) ? (f & 1) : 0;
-        unsigned char* out_tile = out_tiles + b * kOutTileBytes;
-        const unsigned char* stage_a = stages + (b * NSLOT) * slot_bytes;
-        const unsigned char* stage_b = stage_a + S1 * slot_bytes;
-
-        if (f > 0) {
-            // out_tile[b] was last stored by frame f - n_buffers, stage[b] last read by the same frame
-            if (tid == 0) {
-                if (a.n_buffers == 2) ptx::bulk_wait_read1();
+        unsigned v[NSLOT][kPxPerThread];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            if (nbox[s] == 0) {  // block-uniform
+#pragma unroll
+                for (int p = 0; p < kPxPerThread; ++p) v[s][p] = 0;
+                continue;
+            }
+            const int b = (a.n_buffers == 2) ? (t & 1) : 0;
+            ptx::mbarrier_wait(&sh->bar[b], (unsigned)((a.n_buffers == 2 ? (t >> 1) : t) & 1));
+            const unsigned char* stage = stages + b * buf_bytes;
+#pragma unroll
+            for (int p = 0; p < kPxPerThread; ++p) v[s][p] = pick_px(stage, loc[s][p]);
+            // every thread is done with this stage buffer (and, once per frame, the store that last
+            // read this frame's output tile is done with it)
+            if (tid == 0 && s == S1 && f >= a.n_out) {
+                if (a.n_out == 2) ptx::bulk_wait_read1();
                 else ptx::bulk_wait_read0();
             }
             __syncthreads();
-            if (a.n_buffers == 1 && any && tid == 0) issue_loads(f);
+            if (tid == 0 && t + a.n_buffers < n_items) issue_item(t + a.n_buffers);
+            ++t;
         }
-        if (a.n_buffers == 2 && any && tid == 0 && f + 1 < a.n_frames) issue_loads(f + 1);
-        if (any) ptx::mbarrier_wait(&sh->bar[b], (unsigned)((a.n_buffers == 2 ? (f >> 1) : f) & 1));
+        if (n_act == 0 || (NSLOT == 2 && nbox[S1] == 0)) {
+            // the wait above was skipped: still order the reuse of the output tile
+            if (f >= a.n_out) {
+                if (tid == 0) {
+                    if (a.n_out == 2) ptx::bulk_wait_read1();
+                    else ptx::bulk_wait_read0();
+                }
+                __syncthreads();
+            }
+        }
 
+        unsigned char* out_tile = out_tiles + ((a.n_out == 2) ? (f & 1) : 0) * kOutTileBytes;
 #pragma unroll
         for (int q = 0; q < kRowsPerThread; ++q) {
             unsigned px[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int p = q * 4 + k;
-                const unsigned v0 = pick_px(stage_a, loc[0][p]);
                 if (DBL) {
-                    const unsigned v1 = pick_px(stage_b, loc[S1][p]);
                     if (WGT_IN_SMEM) {
                         const double2 w = w_scratch[p * kTileThreads + tid];
-                        px[k] = blend_px(v0, w.x, v1, w.y);
+                        px[k] = blend_px(v[0][p], w.x, v[S1][p], w.y);
                     } else {
-                        px[k] = blend_px(v0, wrow[q][0], v1, wrow[q][1]);
+                        px[k] = blend_px(v[0][p], wrow[q][0], v[S1][p], wrow[q][1]);
                     }
                 } else {
-                    px[k] = v0;
+                    px[k] = v[0][p];
                 }
             }
             store_quad(reinterpret_cast<unsigned*>(out_tile + (rg + q * kRowGroups) * kOutRowBytes + qc * 12), px);
         }
-
         ptx::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
@@ -452,10 +564,9 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 }
 
 template <int SRC_KIND, int MODE>
-inline int tiled_smem_bytes(int stage_pitch, int stage_boxes, int n_buffers) {
+inline int tiled_smem_bytes(int stage_pitch, int stage_boxes, int n_buffers, int n_out) {
     const int nslot = (SRC_KIND == PB_KIND_DOUBLE) ? 2 : 1;
-    int bytes = n_buffers * kOutTileBytes + n_buffers * nslot * (stage_boxes * kBoxRows * stage_pitch + 128) +
-                (int)sizeof(TileShared);
+    int bytes = n_out * kOutTileBytes + n_buffers * (stage_boxes * kBoxRows * stage_pitch + 128) + (int)sizeof(TileShared);
     if (MODE == 0) {
         bytes += nslot * kPxPerThread * kTileThreads * (int)sizeof(int);
         if (SRC_KIND == PB_KIND_DOUBLE) bytes += kPxPerThread * kTileThreads * (int)sizeof(double2);
