@@ -394,7 +394,7 @@ struct pb_plan {
     bool separable;      // un-rotated equirect output, camera / double source
     int stage_pitch;     // bytes per staged source row (TMA box width)
     int stage_boxes;     // 16-row TMA boxes per stage buffer
-    double* tables;      // device: col_tab [W][2] then row_tab [H][4]; null unless separable
+    double* tables;      // device: col_tab [W][2], row_tab [H][4], then the per-tile footprints; null unless separable
     int device;
 };
 
@@ -431,8 +431,65 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
 // Footprint census of a geometry (one probe launch of the tiled kernel, nothing is remapped):
 // picks the smallest staged-row width and box count that hold the footprint of ~all tiles, so that
 // the stage buffers are as small -- and the occupancy as high -- as this geometry allows.
+static int tiles_x(const pb_plan& p) { return (p.out.W + kTileW - 1) / kTileW; }
+static int tiles_y(const pb_plan& p) { return (p.out.H + kTileH - 1) / kTileH; }
+static int footprint_entries(const pb_plan& p) {
+    return tiles_x(p) * tiles_y(p) * (p.src.kind == PB_KIND_DOUBLE ? 2 : 1);
+}
+// col_tab [W][2] + row_tab [H][4] doubles, then one int4 footprint per (tile, slot)
+static size_t table_doubles(const pb_plan& p) {
+    return 2 * (size_t)p.out.W + 4 * (size_t)p.out.H + 2 * (size_t)footprint_entries(p);
+}
+static const int4* footprint_table(const pb_plan& p, const double* tables) {
+    return reinterpret_cast<const int4*>(tables + 2 * (size_t)p.out.W + 4 * (size_t)p.out.H);
+}
+
+static void pick_stage(pb_plan& p, const int* h) {
+    long long tiles = 0;
+    for (int k = 0; k < kProbePitchBins; ++k) tiles += h[k];
+    if (tiles <= 0) return;
+    const long long need = tiles - tiles / 200;  // all but 0.5 % of the tiles
+    long long acc = 0;
+    int pitch_bin = kProbePitchBins - 1, box_bin = kProbeBoxBins - 1;
+    for (int k = 0; k < kProbePitchBins; ++k) {
+        acc += h[k];
+        if (acc >= need) { pitch_bin = k; break; }
+    }
+    acc = 0;
+    for (int k = 0; k < kProbeBoxBins; ++k) {
+        acc += h[kProbePitchBins + k];
+        if (acc >= need) { box_bin = k; break; }
+    }
+    int pitch = 16 * (pitch_bin < 4 ? 4 : pitch_bin), boxes = box_bin < 1 ? 1 : box_bin;
+    if (pitch > 512) pitch = 512;  // u16 tensor map: at most 256 elements per box row
+    while (boxes > 1 && boxes * kBoxRows * pitch > 48 * 1024) --boxes;
+    p.stage_pitch = pitch;
+    p.stage_boxes = boxes;
+}
+
 static void tune_stage(pb_plan& p, cudaStream_t st) {
     if (p.desc.channels != 3) return;
+    if (p.separable && p.tables) {
+        // the per-tile footprints are already on the device: histogram them on the host
+        const int n_entries = footprint_entries(p);
+        int4* host = new (std::nothrow) int4[n_entries];
+        if (!host) return;
+        if (cudaMemcpyAsync(host, footprint_table(p, p.tables), sizeof(int4) * n_entries, cudaMemcpyDeviceToHost, st) ==
+                cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess) {
+            int h[kProbePitchBins + kProbeBoxBins] = {0};
+            for (int e = 0; e < n_entries; ++e) {
+                if (host[e].z == 0) continue;
+                const int pb = ((host[e].w >> 1) + 15) / 16, bb = host[e].z;
+                h[pb < kProbePitchBins - 1 ? pb : kProbePitchBins - 1] += 1;
+                h[kProbePitchBins + (bb < kProbeBoxBins - 1 ? bb : kProbeBoxBins - 1)] += 1;
+            }
+            pick_stage(p, h);
+        } else {
+            (void)cudaGetLastError();
+        }
+        delete[] host;
+        return;
+    }
     int* census = nullptr;
     const int n = kProbePitchBins + kProbeBoxBins;
     if (cudaMalloc((void**)&census, n * sizeof(int)) != cudaSuccess) {
@@ -458,38 +515,27 @@ static void tune_stage(pb_plan& p, cudaStream_t st) {
     if (launch_tiled(a, p.separable && p.tables != nullptr, st) == cudaSuccess &&
         cudaMemcpyAsync(h, census, sizeof(h), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
         cudaStreamSynchronize(st) == cudaSuccess) {
-        long long tiles = 0;
-        for (int k = 0; k < kProbePitchBins; ++k) tiles += h[k];
-        if (tiles > 0) {
-            const long long need = tiles - tiles / 200;  // all but 0.5 % of the tiles
-            long long acc = 0;
-            int pitch_bin = kProbePitchBins - 1, box_bin = kProbeBoxBins - 1;
-            for (int k = 0; k < kProbePitchBins; ++k) {
-                acc += h[k];
-                if (acc >= need) { pitch_bin = k; break; }
-            }
-            acc = 0;
-            for (int k = 0; k < kProbeBoxBins; ++k) {
-                acc += h[kProbePitchBins + k];
-                if (acc >= need) { box_bin = k; break; }
-            }
-            int pitch = 16 * (pitch_bin < 4 ? 4 : pitch_bin), boxes = box_bin < 1 ? 1 : box_bin;
-            if (pitch > 512) pitch = 512;             // u16 tensor map: at most 256 elements per box row
-            while (boxes > 1 && boxes * kBoxRows * pitch > 48 * 1024) --boxes;
-            p.stage_pitch = pitch;
-            p.stage_boxes = boxes;
-        }
+        pick_stage(p, h);
     } else {
         (void)cudaGetLastError();
     }
     cudaFree(census);
 }
 
-static size_t table_doubles(const pb_plan& p) { return 2 * (size_t)p.out.W + 4 * (size_t)p.out.H; }
-
 static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st) {
     const int n = p.out.W > p.out.H ? p.out.W : p.out.H;
     pb_tables_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.out, p.src, tables, tables + 2 * (size_t)p.out.W);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    TiledArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.out = p.out;
+    a.src = p.src;
+    a.col_tab = tables;
+    a.row_tab = tables + 2 * (size_t)p.out.W;
+    const int n_entries = footprint_entries(p);
+    pb_footprint_kernel<<<(n_entries + 7) / 8, 256, 0, st>>>(a, const_cast<int4*>(footprint_table(p, tables)),
+                                                           tiles_x(p), n_entries);
     return cudaGetLastError();
 }
 
@@ -510,6 +556,7 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         a.rot = p.rot;
         a.col_tab = tables;
         a.row_tab = tables ? tables + 2 * (size_t)p.out.W : nullptr;
+        a.tile_fp = tables ? footprint_table(p, tables) : nullptr;
         a.src_px = src;
         a.src_frame_stride = src_frame_stride;
         a.n_frames = n_frames;

@@ -66,6 +66,7 @@ struct TiledArgs {
     int n_buffers;    // stage buffers: 1, or 2 (loads of the next item overlap the current gather)
     int n_out;        // output tile buffers: 1, or 2 (the store of frame f overlaps frame f+1)
     int* probe;       // non-null: footprint census only (see pb_plan_create), nothing is remapped
+    const int4* tile_fp;  // separable: per (tile, slot) footprint {by0, xb0, nbox, all_valid | need_bytes << 1}
 };
 
 // footprint census written by a probe launch: how many tiles need a staged row of k*16 bytes
@@ -109,7 +110,6 @@ __global__ void __launch_bounds__(256) pb_tables_kernel(const __grid_constant__ 
 struct alignas(16) TileShared {
     uint64_t bar[2];  // one mbarrier per stage buffer
     int min_x[2], max_x[2], min_y[2], max_y[2];
-    int all_valid[2];
 };
 
 __device__ __forceinline__ unsigned pick_px(const unsigned char* __restrict__ stage, int b) {
@@ -226,6 +226,30 @@ __device__ __forceinline__ void separable_footprint(const TiledArgs& a, int slot
     all_valid = __all_sync(0xffffffffu, inside) && !any_nan;
 }
 
+// Footprints of every (tile, slot) of a separable geometry, one warp each; they depend on the
+// geometry only, so a plan computes them once (pb_plan_create) and every launch just reads them.
+__global__ void __launch_bounds__(256) pb_footprint_kernel(const __grid_constant__ TiledArgs a, int4* __restrict__ tile_fp,
+                                                           int tiles_x, int n_entries) {
+    const int nslot = (a.src.kind == PB_KIND_DOUBLE) ? 2 : 1;
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);  // entry = tile * nslot + slot
+    if (e >= n_entries) return;
+    const int tile = e / nslot, slot = e - tile * nslot;
+    const int x0 = (tile % tiles_x) * kTileW, y0 = (tile / tiles_x) * kTileH;
+    Footprint fp;
+    bool all_valid;
+    separable_footprint(a, slot, x0, y0, threadIdx.x & 31, fp, all_valid);
+    if ((threadIdx.x & 31) == 0) {
+        int4 v = make_int4(0, 0, 0, 0);
+        if (fp.mxx >= 0) {
+            v.x = fp.mny;
+            v.y = (fp.mnx * 3) & ~15;  // TMA: first byte of a box row on a 16-byte boundary
+            v.z = (fp.mxy - fp.mny + kBoxRows) / kBoxRows;
+            v.w = (all_valid ? 1 : 0) | ((fp.mxx * 3 + 3 - v.y) << 1);
+        }
+        tile_fp[e] = v;
+    }
+}
+
 // Slow path of a tile whose footprint cannot be staged (it holds a pole of the source, straddles
 // the +-pi seam of a panorama, or is simply too wide): every pixel is resolved again and read
 // straight from global memory.  Rare by construction; clarity over speed.
@@ -335,28 +359,35 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             sh->min_y[s] = 0x7fffffff;
             sh->max_x[s] = -1;
             sh->max_y[s] = -1;
-            sh->all_valid[s] = 0;
         }
     }
     if (tid < a.n_buffers * 8)
         reinterpret_cast<int4*>(stages + (tid >> 3) * buf_bytes + ztail)[tid & 7] = make_int4(0, 0, 0, 0);
-    __syncthreads();
 
     // ---------------------------------------------------------------- 1. resolve (generic)  2. footprint
+    // separable: start the table loads now, they are consumed after the barrier
+    double2 cs[4], r01[kRowsPerThread];
+    double wrow[kRowsPerThread][2];  // separable double source: blend weights per row
+    int4 fpv[NSLOT];
     if (MODE == 1) {
-        if (tid < 32 * NSLOT) {  // warp s works out the footprint of slot s
-            Footprint fp;
-            bool all_valid;
-            separable_footprint(a, tid >> 5, x0, y0, tid & 31, fp, all_valid);
-            if ((tid & 31) == 0) {
-                sh->min_x[tid >> 5] = fp.mnx;
-                sh->min_y[tid >> 5] = fp.mny;
-                sh->max_x[tid >> 5] = fp.mxx;
-                sh->max_y[tid >> 5] = fp.mxy;
-                sh->all_valid[tid >> 5] = all_valid;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) fpv[s] = __ldg(a.tile_fp + (blockIdx.y * gridDim.x + blockIdx.x) * NSLOT + s);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cs[k] = __ldg(reinterpret_cast<const double2*>(a.col_tab) + min(jx + k, a.out.W - 1));
+#pragma unroll
+        for (int q = 0; q < kRowsPerThread; ++q) {
+            // rows past the image edge repeat the last row: they widen nothing and TMA clips them
+            const int i = min(y0 + rg + q * kRowGroups, a.out.H - 1);
+            r01[q] = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i);
+            if (DBL) {
+                const double2 r23 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i + 1);
+                wrow[q][0] = r23.x;
+                wrow[q][1] = r23.y;
             }
         }
+        __syncthreads();  // barrier init + zeroed tails visible
     } else {
+        __syncthreads();  // barrier init + zeroed tails + footprint accumulators visible
         // generic rays: heavy float64 code, kept rolled (results parked in shared memory)
         Footprint fp[NSLOT];
 #pragma unroll
@@ -386,26 +417,40 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                 atomicMax(&sh->max_y[s], fp[s].mxy);
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
 
     // rectangle of slot s: rows [by0, by0 + 16*nbox), bytes [xb0, xb0 + stage_pitch) of each row
     int by0[NSLOT], xb0[NSLOT], nbox[NSLOT];
+    bool all_valid[NSLOT];
     bool staged = true;
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
+        int need_bytes = 0;
         by0[s] = xb0[s] = nbox[s] = 0;
-        const int hi_x = sh->max_x[s];
-        if (hi_x < 0) continue;
-        by0[s] = sh->min_y[s];
-        // TMA needs the first byte of a box row on a 16-byte boundary (measured: any other start
-        // faults with "illegal instruction", profiles/microbench/tma_probe.cu)
-        xb0[s] = (sh->min_x[s] * 3) & ~15;
-        nbox[s] = (sh->max_y[s] - by0[s] + kBoxRows) / kBoxRows;
+        all_valid[s] = false;
+        if (MODE == 1) {
+            by0[s] = fpv[s].x;
+            xb0[s] = fpv[s].y;
+            nbox[s] = fpv[s].z;
+            all_valid[s] = fpv[s].w & 1;
+            need_bytes = fpv[s].w >> 1;
+        } else {
+            const int hi_x = sh->max_x[s];
+            if (hi_x >= 0) {
+                by0[s] = sh->min_y[s];
+                // TMA needs the first byte of a box row on a 16-byte boundary (measured: any other
+                // start faults with "illegal instruction", profiles/microbench/tma_probe.cu)
+                xb0[s] = (sh->min_x[s] * 3) & ~15;
+                nbox[s] = (sh->max_y[s] - by0[s] + kBoxRows) / kBoxRows;
+                need_bytes = hi_x * 3 + 3 - xb0[s];
+            }
+        }
+        if (nbox[s] == 0) continue;
         // (the funnel-shift gather may read a few bytes past a pixel: the next row, or the tail)
-        if (nbox[s] > a.stage_boxes || hi_x * 3 + 3 - xb0[s] > a.stage_pitch) staged = false;
+        if (nbox[s] > a.stage_boxes || need_bytes > a.stage_pitch) staged = false;
         if (a.probe != nullptr && tid == 0) {
-            atomicAdd(a.probe + min((hi_x * 3 + 3 - xb0[s] + 15) / 16, kProbePitchBins - 1), 1);
+            atomicAdd(a.probe + min((need_bytes + 15) / 16, kProbePitchBins - 1), 1);
             atomicAdd(a.probe + kProbePitchBins + min(nbox[s], kProbeBoxBins - 1), 1);
         }
     }
@@ -418,23 +463,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     // ---------------------------------------------------------------- 1. resolve (separable) -> byte offsets
     // loc = byte offset of the pixel inside the staged rectangle of its slot (ztail: no source)
     int loc[NSLOT][kPxPerThread];
-    double wrow[kRowsPerThread][2];  // separable double source: blend weights per row
     if (MODE == 1) {
-        double2 cs[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) cs[k] = __ldg(reinterpret_cast<const double2*>(a.col_tab) + min(jx + k, a.out.W - 1));
-        double2 r01[kRowsPerThread];
-#pragma unroll
-        for (int q = 0; q < kRowsPerThread; ++q) {
-            // rows past the image edge repeat the last row: they widen nothing and TMA clips them
-            const int i = min(y0 + rg + q * kRowGroups, a.out.H - 1);
-            r01[q] = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i);
-            if (DBL) {
-                const double2 r23 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i + 1);
-                wrow[q][0] = r23.x;
-                wrow[q][1] = r23.y;
-            }
-        }
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
             const int w = DBL ? (s ? a.src.wr : a.src.wl) : a.src.W;
@@ -443,7 +472,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             if (nbox[s] == 0) {  // nothing of this slot is visible from the tile
 #pragma unroll
                 for (int p = 0; p < kPxPerThread; ++p) loc[s][p] = ztail;
-            } else if (sh->all_valid[s]) {  // every pixel lands inside the source: no bounds tests
+            } else if (all_valid[s]) {  // every pixel lands inside the source: no bounds tests
 #pragma unroll
                 for (int q = 0; q < kRowsPerThread; ++q)
 #pragma unroll
