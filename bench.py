@@ -366,10 +366,9 @@ def run_gpu(args):
     e2e_dt, h2d, d2h, e2e_launches, _, _ = timed_e2e_steps(
         torch, source, cmap, name, frames, max(1, args.e2e_steps), args.warmup, dist)
 
-    times = torch.tensor([total_ms, e2e_dt * 1e3], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)  # timing only: max over ranks
-    total_ms, e2e_ms = (float(v) for v in times.cpu())
+    from photonbend_b200.batch import max_over_ranks
+
+    total_ms, e2e_ms = max_over_ranks([total_ms, e2e_dt * 1e3], device="cuda")  # timing only
 
     info = golden_info(name)
     px_per_step = info["out_pixels"] * frames * world

@@ -28,6 +28,18 @@ def shard_frames(n_frames: int, rank: int, world_size: int) -> range:
     return range(rank, n_frames, world_size)
 
 
+def max_over_ranks(values, device="cpu"):
+    """Element-wise max of a list of floats over all ranks of the default process group (a
+    timing reduction only -- the remap itself exchanges nothing between GPUs)."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.cpu()]
+
+
 def remap_batch(source, coordinate_map: CoordinateMap, frames, out=None):
     """Remap a device batch ``frames`` (uint8 CUDA tensor (N, H, W, C)) that shares the geometry
     of ``source`` (a CameraImage / DoubleCameraImage / PanoramaImage whose own ``image`` is only

@@ -318,7 +318,7 @@ __device__ __noinline__ void direct_tile(const TiledArgs& a, const int* xy_scrat
 
 // MODE: 0 = generic per-pixel rays (any output, any rotations), 1 = separable tables
 template <int OUT_KIND, int SRC_KIND, int MODE>
-__global__ void __launch_bounds__(kTileThreads, (MODE == 1) ? 3 : 2)
+__global__ void __launch_bounds__(kTileThreads, (MODE == 1) ? ((SRC_KIND == PB_KIND_DOUBLE) ? 3 : 5) : 2)
 remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     constexpr int NSLOT = (SRC_KIND == PB_KIND_DOUBLE) ? 2 : 1;
     constexpr int S1 = NSLOT - 1;  // index of the second slot (aliases the first when there is none)
@@ -460,6 +460,23 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         return;
     }
 
+    // ---------------------------------------------------------------- 3. stage (issued first: the loads fly while the offsets are resolved)
+    // items = (frame, active slot) pairs, in order; item t uses stage buffer t % n_buffers
+    const int first = (nbox[0] > 0) ? 0 : S1;
+    const int n_act = (nbox[0] > 0) + ((NSLOT == 2 && nbox[S1] > 0) ? 1 : 0);
+    const int n_items = a.n_frames * n_act;
+    auto issue_item = [&](int t) {  // one thread
+        const int b = (a.n_buffers == 2) ? (t & 1) : 0;
+        const int s = (n_act == 2) ? (t & 1) : first;
+        const int f = (n_act == 2) ? (t >> 1) : t;
+        ptx::mbarrier_arrive_expect_tx(&sh->bar[b], (unsigned)(nbox[s] * kBoxRows * a.stage_pitch));
+        for (int k = 0; k < nbox[s]; ++k)
+            ptx::tma_load_3d(stages + b * buf_bytes + k * kBoxRows * a.stage_pitch, &a.src_map, xb0[s] >> 1,
+                             by0[s] + k * kBoxRows, f, &sh->bar[b]);
+    };
+    if (tid == 0)
+        for (int t = 0; t < min(a.n_buffers, n_items); ++t) issue_item(t);
+
     // ---------------------------------------------------------------- 1. resolve (separable) -> byte offsets
     // loc = byte offset of the pixel inside the staged rectangle of its slot (ztail: no source)
     int loc[NSLOT][kPxPerThread];
@@ -509,23 +526,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         }
     }
 
-    // ---------------------------------------------------------------- 3. stage  4. gather  5. store
-    // items = (frame, active slot) pairs, in order; item t uses stage buffer t % n_buffers
-    const int first = (nbox[0] > 0) ? 0 : S1;
-    const int n_act = (nbox[0] > 0) + ((NSLOT == 2 && nbox[S1] > 0) ? 1 : 0);
-    const int n_items = a.n_frames * n_act;
-    auto issue_item = [&](int t) {  // one thread
-        const int b = (a.n_buffers == 2) ? (t & 1) : 0;
-        const int s = (n_act == 2) ? (t & 1) : first;
-        const int f = (n_act == 2) ? (t >> 1) : t;
-        ptx::mbarrier_arrive_expect_tx(&sh->bar[b], (unsigned)(nbox[s] * kBoxRows * a.stage_pitch));
-        for (int k = 0; k < nbox[s]; ++k)
-            ptx::tma_load_3d(stages + b * buf_bytes + k * kBoxRows * a.stage_pitch, &a.src_map, xb0[s] >> 1,
-                             by0[s] + k * kBoxRows, f, &sh->bar[b]);
-    };
-    if (tid == 0)
-        for (int t = 0; t < min(a.n_buffers, n_items); ++t) issue_item(t);
-
+    // ---------------------------------------------------------------- 4. gather  5. store
     int t = 0;
     for (int f = 0; f < a.n_frames; ++f) {
         unsigned v[NSLOT][kPxPerThread];

@@ -1,0 +1,69 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/pb_remap.h
+declares; argument errors come back as codes + messages without touching a GPU."""
+
+import ctypes
+import os
+import re
+
+from conftest import REPO
+
+
+def _declared_functions():
+    with open(os.path.join(REPO, "include", "pb_remap.h")) as fh:
+        text = fh.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    from photonbend_b200 import _native
+
+    declared = _declared_functions()
+    assert declared, "no functions found in include/pb_remap.h"
+    assert sorted(_native.EXPORTS) == declared
+
+
+def test_library_exports_every_declared_symbol():
+    from photonbend_b200 import _native
+
+    lib = _native.load()
+    for name in _declared_functions():
+        assert hasattr(lib, name), name
+    assert lib.pb_version() == 1
+
+
+def test_struct_layout_matches_header():
+    from photonbend_b200 import _native
+
+    assert ctypes.sizeof(_native.ImageDesc) == 32
+    assert ctypes.sizeof(_native.RemapDesc) == 2 * 32 + 8 + _native.PB_MAX_ROTATIONS * 9 * 8
+    assert _native.RemapDesc.rotations.offset == 72
+
+
+def test_argument_errors_need_no_gpu():
+    from photonbend_b200 import _native
+
+    lib = _native.load()
+    d = _native.RemapDesc()
+    assert lib.pb_remap_u8(ctypes.byref(d), None, 0, None, 0, 1, None) == _native.PB_ERR_INVALID_ARGUMENT
+    assert b"null" in lib.pb_last_error()
+    fake = ctypes.c_void_p(256)  # never dereferenced: validation fails first
+    d.out.kind, d.out.height, d.out.width = _native.KIND_EQUIRECT, 0, 10
+    assert lib.pb_remap_u8(ctypes.byref(d), fake, 0, fake, 0, 1, None) == _native.PB_ERR_INVALID_ARGUMENT
+    assert b"positive" in lib.pb_last_error()
+    d.out.height = 8
+    d.src.kind, d.src.height, d.src.width, d.src.lens = _native.KIND_CAMERA, 8, 8, 99
+    assert lib.pb_remap_u8(ctypes.byref(d), fake, 0, fake, 0, 1, None) == _native.PB_ERR_INVALID_ARGUMENT
+    assert b"lens" in lib.pb_last_error()
+    d.src.lens, d.channels, d.n_rotations = 0, 3, _native.PB_MAX_ROTATIONS + 1
+    assert lib.pb_remap_u8(ctypes.byref(d), fake, 0, fake, 0, 1, None) == _native.PB_ERR_TOO_MANY_ROTATIONS
+    d.n_rotations, d.channels = 0, 9
+    assert lib.pb_remap_u8(ctypes.byref(d), fake, 0, fake, 0, 1, None) == _native.PB_ERR_UNSUPPORTED
+    d.channels = 3
+    assert lib.pb_remap_u8(ctypes.byref(d), fake, 0, fake, 0, 0, None) == _native.PB_OK  # zero frames: nothing to do
+    img = _native.ImageDesc()
+    img.kind, img.height, img.width = _native.KIND_DOUBLE, 10, 11
+    assert lib.pb_output_width(ctypes.byref(img)) == 10
+    handle = ctypes.c_void_p()
+    assert lib.pb_plan_create(None, None, ctypes.byref(handle)) == _native.PB_ERR_INVALID_ARGUMENT
+    lib.pb_plan_destroy(None)  # destroying nothing is allowed
