@@ -88,6 +88,36 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, int c0, int c1, i
                  : "memory");
 }
 
+// L2 eviction-priority policies for bulk copies: the source is re-read by neighbouring tiles
+// (keep it), the output is written once (let it go first)
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+            smem_addr(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar)), "l"(policy)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d_hint(const void* tmap, int c0, int c1, int c2, const void* smem_src,
+                                                  uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(smem_src)), "l"(policy)
+                 : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }

@@ -470,9 +470,10 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         const int s = (n_act == 2) ? (t & 1) : first;
         const int f = (n_act == 2) ? (t >> 1) : t;
         ptx::mbarrier_arrive_expect_tx(&sh->bar[b], (unsigned)(nbox[s] * kBoxRows * a.stage_pitch));
+        const uint64_t keep = ptx::policy_evict_last();
         for (int k = 0; k < nbox[s]; ++k)
-            ptx::tma_load_3d(stages + b * buf_bytes + k * kBoxRows * a.stage_pitch, &a.src_map, xb0[s] >> 1,
-                             by0[s] + k * kBoxRows, f, &sh->bar[b]);
+            ptx::tma_load_3d_hint(stages + b * buf_bytes + k * kBoxRows * a.stage_pitch, &a.src_map, xb0[s] >> 1,
+                                  by0[s] + k * kBoxRows, f, &sh->bar[b], keep);
     };
     if (tid == 0)
         for (int t = 0; t < min(a.n_buffers, n_items); ++t) issue_item(t);
@@ -529,19 +530,33 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     // ---------------------------------------------------------------- 4. gather  5. store
     int t = 0;
     for (int f = 0; f < a.n_frames; ++f) {
-        unsigned v[NSLOT][kPxPerThread];
+        // v = the frame's pixels: slot 0 as gathered, then (double source) blended with slot 1 in place
+        unsigned v[kPxPerThread];
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
-            if (nbox[s] == 0) {  // block-uniform
+            if (nbox[s] == 0) {  // block-uniform: this slot contributes black
 #pragma unroll
-                for (int p = 0; p < kPxPerThread; ++p) v[s][p] = 0;
+                for (int p = 0; p < kPxPerThread; ++p) {
+                    if (s == 0) v[p] = 0;
+                    else if (WGT_IN_SMEM) {
+                        const double2 w = w_scratch[p * kTileThreads + tid];
+                        v[p] = blend_px(v[p], w.x, 0u, w.y);
+                    } else v[p] = blend_px(v[p], wrow[p >> 2][0], 0u, wrow[p >> 2][1]);
+                }
                 continue;
             }
             const int b = (a.n_buffers == 2) ? (t & 1) : 0;
             ptx::mbarrier_wait(&sh->bar[b], (unsigned)((a.n_buffers == 2 ? (t >> 1) : t) & 1));
             const unsigned char* stage = stages + b * buf_bytes;
 #pragma unroll
-            for (int p = 0; p < kPxPerThread; ++p) v[s][p] = pick_px(stage, loc[s][p]);
+            for (int p = 0; p < kPxPerThread; ++p) {
+                const unsigned g = pick_px(stage, loc[s][p]);
+                if (s == 0) v[p] = g;
+                else if (WGT_IN_SMEM) {
+                    const double2 w = w_scratch[p * kTileThreads + tid];
+                    v[p] = blend_px(v[p], w.x, g, w.y);
+                } else v[p] = blend_px(v[p], wrow[p >> 2][0], g, wrow[p >> 2][1]);
+            }
             // every thread is done with this stage buffer (and, once per frame, the store that last
             // read this frame's output tile is done with it)
             if (tid == 0 && s == S1 && f >= a.n_out) {
@@ -565,28 +580,12 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 
         unsigned char* out_tile = out_tiles + ((a.n_out == 2) ? (f & 1) : 0) * kOutTileBytes;
 #pragma unroll
-        for (int q = 0; q < kRowsPerThread; ++q) {
-            unsigned px[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int p = q * 4 + k;
-                if (DBL) {
-                    if (WGT_IN_SMEM) {
-                        const double2 w = w_scratch[p * kTileThreads + tid];
-                        px[k] = blend_px(v[0][p], w.x, v[S1][p], w.y);
-                    } else {
-                        px[k] = blend_px(v[0][p], wrow[q][0], v[S1][p], wrow[q][1]);
-                    }
-                } else {
-                    px[k] = v[0][p];
-                }
-            }
-            store_quad(reinterpret_cast<unsigned*>(out_tile + (rg + q * kRowGroups) * kOutRowBytes + qc * 12), px);
-        }
+        for (int q = 0; q < kRowsPerThread; ++q)
+            store_quad(reinterpret_cast<unsigned*>(out_tile + (rg + q * kRowGroups) * kOutRowBytes + qc * 12), v + q * 4);
         ptx::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
-            ptx::tma_store_3d(&a.dst_map, x0 * 3, y0, f, out_tile);
+            ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, y0, f, out_tile, ptx::policy_evict_first());
             ptx::bulk_commit();
         }
     }
