@@ -5,6 +5,7 @@
 //        -Xcompiler -fPIC,-ffp-contract=off -shared -Iinclude -o libpbremap.so pb_remap.cu
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -354,8 +355,7 @@ static cudaError_t launch_tiled_one(const TiledArgs& a, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    dim3 grid((a.out.W + kTileW - 1) / kTileW, (a.out.H + kTileH - 1) / kTileH);
-    remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE><<<grid, kTileThreads, smem, st>>>(a);
+    remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE><<<a.tiles_x * a.tiles_y, kTileThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -394,6 +394,7 @@ struct pb_plan {
     bool separable;      // un-rotated equirect output, camera / double source
     int stage_pitch;     // bytes per staged source row (TMA box width)
     int stage_boxes;     // 16-row TMA boxes per stage buffer
+    int raster_band;     // tile rows per raster band (see remap_tiled_kernel)
     double* tables;      // device: col_tab [W][2], row_tab [H][4], then the per-tile footprints; null unless separable
     int device;
 };
@@ -422,8 +423,10 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     std::memcpy(p.rot.m, d.rotations, sizeof(p.rot.m));
     p.separable = d.out.kind == PB_KIND_EQUIRECT && d.n_rotations == 0 && d.src.kind != PB_KIND_EQUIRECT &&
                   d.channels == 3;
-    p.stage_pitch = 288;  // 96 source pixels
+    p.stage_pitch = 304;  // 101 source pixels; an odd number of 16-byte units (see pick_stage)
     p.stage_boxes = 6;    // 96 source rows
+    p.raster_band = 16;
+    if (const char* e = std::getenv("PB_RASTER_BAND")) p.raster_band = std::atoi(e);  // tuning experiments
     p.tables = nullptr;
     p.device = -1;
 }
@@ -460,8 +463,14 @@ static void pick_stage(pb_plan& p, const int* h) {
         acc += h[kProbePitchBins + k];
         if (acc >= need) { box_bin = k; break; }
     }
-    int pitch = 16 * (pitch_bin < 4 ? 4 : pitch_bin), boxes = box_bin < 1 ? 1 : box_bin;
-    if (pitch > 512) pitch = 512;  // u16 tensor map: at most 256 elements per box row
+    // An odd number of 16-byte units per staged row: vertically adjacent source pixels then sit
+    // 4*odd banks apart (8 distinct bank groups) instead of piling onto 1-4 of them, which is what
+    // the gather of a tile whose footprint runs down the source image would otherwise do
+    // (tests/analysis/stage_sim.py: 4.4 -> 2.3 wavefronts per LDS at pitch 256 -> 272).
+    int units = pitch_bin < 5 ? 5 : pitch_bin, boxes = box_bin < 1 ? 1 : box_bin;
+    if (units % 2 == 0 && !std::getenv("PB_PITCH_EVEN")) ++units;
+    if (units > 31) units = 31;  // u16 tensor map: at most 256 elements per box row
+    int pitch = 16 * units;
     while (boxes > 1 && boxes * kBoxRows * pitch > 48 * 1024) --boxes;
     p.stage_pitch = pitch;
     p.stage_boxes = boxes;
@@ -511,6 +520,9 @@ static void tune_stage(pb_plan& p, cudaStream_t st) {
     a.n_buffers = 1;
     a.n_out = 1;
     a.probe = census;
+    a.tiles_x = tiles_x(p);
+    a.tiles_y = tiles_y(p);
+    a.raster_band = 0;
     int h[kProbePitchBins + kProbeBoxBins];
     if (launch_tiled(a, p.separable && p.tables != nullptr, st) == cudaSuccess &&
         cudaMemcpyAsync(h, census, sizeof(h), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
@@ -561,6 +573,9 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         a.src_frame_stride = src_frame_stride;
         a.n_frames = n_frames;
         a.src_pitch = (int)src_pitch;
+        a.tiles_x = tiles_x(p);
+        a.tiles_y = tiles_y(p);
+        a.raster_band = p.raster_band;
         // stage geometry: one column of 16-row TMA boxes per slot
         const bool dbl = p.src.kind == PB_KIND_DOUBLE;
         a.stage_pitch = p.stage_pitch;

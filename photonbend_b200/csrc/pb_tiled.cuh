@@ -66,6 +66,8 @@ struct TiledArgs {
     int n_buffers;    // stage buffers: 1, or 2 (loads of the next item overlap the current gather)
     int n_out;        // output tile buffers: 1, or 2 (the store of frame f overlaps frame f+1)
     int* probe;       // non-null: footprint census only (see pb_plan_create), nothing is remapped
+    int tiles_x, tiles_y;  // tiles per output row / column
+    int raster_band;  // CTAs walk bands of this many tile rows column by column (0: plain row-major)
     const int4* tile_fp;  // separable: per (tile, slot) footprint {by0, xb0, nbox, all_valid | need_bytes << 1}
 };
 
@@ -112,11 +114,16 @@ struct alignas(16) TileShared {
     int min_x[2], max_x[2], min_y[2], max_y[2];
 };
 
-__device__ __forceinline__ unsigned pick_px(const unsigned char* __restrict__ stage, int b) {
+__device__ __forceinline__ unsigned pick_px(unsigned stage_sa, int b) {
     // the 3 bytes at byte offset b of the staged rectangle (+ one byte of garbage on top): two
-    // aligned words and a funnel shift; SHF takes its shift count modulo 32, so b * 8 does
-    const unsigned* w = reinterpret_cast<const unsigned*>(stage + (b & ~3));
-    return __funnelshift_r(w[0], w[1], b << 3);
+    // aligned words and a funnel shift; SHF takes its shift count modulo 32, so b * 8 does.
+    // stage_sa is the (block-uniform) shared-window address of the stage buffer: the loads come
+    // out as LDS [R + UR], without a per-pixel address add.
+    const unsigned addr = stage_sa + (unsigned)(b & ~3);
+    unsigned lo, hi;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lo) : "r"(addr));
+    asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(hi) : "r"(addr));
+    return __funnelshift_r(lo, hi, b << 3);
 }
 
 __device__ __forceinline__ unsigned pick_px_global(const unsigned char* __restrict__ img, int b) {
@@ -341,8 +348,23 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     const int tid = threadIdx.x;
     const int qc = tid & (kQuadsPerRow - 1);
     const int rg = tid >> 3;
-    const int x0 = blockIdx.x * kTileW;
-    const int y0 = blockIdx.y * kTileH;
+    // CTA -> tile.  CTAs are dispatched in blockIdx order, so the tiles that are in flight together
+    // should form a compact 2-D patch of the output: their source footprints overlap, and what one
+    // CTA pulled into L2 is still there when its neighbours ask for it.  Bands of raster_band tile
+    // rows, walked column by column (the last band may be shorter).
+    int tile_x, tile_y;
+    if (a.raster_band > 0) {
+        const int per_band = a.raster_band * a.tiles_x;
+        const int band = blockIdx.x / per_band, within = blockIdx.x - band * per_band;
+        const int bh = min(a.raster_band, a.tiles_y - band * a.raster_band);
+        tile_x = within / bh;
+        tile_y = band * a.raster_band + (within - tile_x * bh);
+    } else {
+        tile_y = blockIdx.x / a.tiles_x;
+        tile_x = blockIdx.x - tile_y * a.tiles_x;
+    }
+    const int x0 = tile_x * kTileW;
+    const int y0 = tile_y * kTileH;
     const int jx = x0 + 4 * qc;
 
     if (tid == 0) {
@@ -371,7 +393,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     int4 fpv[NSLOT];
     if (MODE == 1) {
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s) fpv[s] = __ldg(a.tile_fp + (blockIdx.y * gridDim.x + blockIdx.x) * NSLOT + s);
+        for (int s = 0; s < NSLOT; ++s) fpv[s] = __ldg(a.tile_fp + (tile_y * a.tiles_x + tile_x) * NSLOT + s);
 #pragma unroll
         for (int k = 0; k < 4; ++k) cs[k] = __ldg(reinterpret_cast<const double2*>(a.col_tab) + min(jx + k, a.out.W - 1));
 #pragma unroll
@@ -528,6 +550,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     }
 
     // ---------------------------------------------------------------- 4. gather  5. store
+    const unsigned stages_sa = ptx::smem_addr(stages);
     int t = 0;
     for (int f = 0; f < a.n_frames; ++f) {
         // v = the frame's pixels: slot 0 as gathered, then (double source) blended with slot 1 in place
@@ -547,10 +570,10 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             }
             const int b = (a.n_buffers == 2) ? (t & 1) : 0;
             ptx::mbarrier_wait(&sh->bar[b], (unsigned)((a.n_buffers == 2 ? (t >> 1) : t) & 1));
-            const unsigned char* stage = stages + b * buf_bytes;
+            const unsigned stage_sa = stages_sa + b * buf_bytes;
 #pragma unroll
             for (int p = 0; p < kPxPerThread; ++p) {
-                const unsigned g = pick_px(stage, loc[s][p]);
+                const unsigned g = pick_px(stage_sa, loc[s][p]);
                 if (s == 0) v[p] = g;
                 else if (WGT_IN_SMEM) {
                     const double2 w = w_scratch[p * kTileThreads + tid];
