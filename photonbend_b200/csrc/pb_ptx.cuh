@@ -118,6 +118,14 @@ __device__ __forceinline__ void tma_store_3d_hint(const void* tmap, int c0, int 
                  : "memory");
 }
 
+// TMA tensor-map 3-D box prefetch: global -> L2 only (no shared memory, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }

@@ -67,6 +67,7 @@ struct TiledArgs {
     int n_out;        // output tile buffers: 1, or 2 (the store of frame f overlaps frame f+1)
     int* probe;       // non-null: footprint census only (see pb_plan_create), nothing is remapped
     int tiles_x, tiles_y;  // tiles per output row / column
+    int l2_ahead;     // items whose boxes are prefetched into L2 ahead of the shared-memory loads
     int raster_band;  // CTAs walk bands of this many tile rows column by column (0: plain row-major)
     const int4* tile_fp;  // separable: per (tile, slot) footprint {by0, xb0, nbox, all_valid | need_bytes << 1}
 };
@@ -497,8 +498,18 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             ptx::tma_load_3d_hint(stages + b * buf_bytes + k * kBoxRows * a.stage_pitch, &a.src_map, xb0[s] >> 1,
                                   by0[s] + k * kBoxRows, f, &sh->bar[b], keep);
     };
-    if (tid == 0)
+    // DRAM latency is hidden one level up: the boxes of the items l2_ahead further on are pulled
+    // into L2 by prefetches (they need no shared memory), so the loads proper mostly hit L2
+    auto prefetch_item = [&](int t) {  // one thread
+        const int s = (n_act == 2) ? (t & 1) : first;
+        const int f = (n_act == 2) ? (t >> 1) : t;
+        for (int k = 0; k < nbox[s]; ++k)
+            ptx::tma_prefetch_l2_3d(&a.src_map, xb0[s] >> 1, by0[s] + k * kBoxRows, f);
+    };
+    if (tid == 0) {
         for (int t = 0; t < min(a.n_buffers, n_items); ++t) issue_item(t);
+        for (int t = a.n_buffers; t < min(a.n_buffers + a.l2_ahead, n_items); ++t) prefetch_item(t);
+    }
 
     // ---------------------------------------------------------------- 1. resolve (separable) -> byte offsets
     // loc = byte offset of the pixel inside the staged rectangle of its slot (ztail: no source)
@@ -587,7 +598,10 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                 else ptx::bulk_wait_read0();
             }
             __syncthreads();
-            if (tid == 0 && t + a.n_buffers < n_items) issue_item(t + a.n_buffers);
+            if (tid == 0) {
+                if (t + a.n_buffers < n_items) issue_item(t + a.n_buffers);
+                if (a.l2_ahead > 0 && t + a.n_buffers + a.l2_ahead < n_items) prefetch_item(t + a.n_buffers + a.l2_ahead);
+            }
             ++t;
         }
         if (n_act == 0 || (NSLOT == 2 && nbox[S1] == 0)) {
