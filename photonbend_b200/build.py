@@ -47,7 +47,8 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO, "include"), "-I", CSRC,
+    extra = os.environ.get("PB_NVCC_EXTRA", "").split()  # e.g. -DPB_EXPERIMENTS for timing experiments
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(REPO, "include"), "-I", CSRC,
            "-o", LIB_PATH, *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

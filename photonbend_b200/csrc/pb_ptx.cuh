@@ -130,6 +130,44 @@ __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
 
+// shared-memory counter shared by the warps of a block: the add releases this warp's reads of a
+// stage buffer and acquires those of the warps that counted before it
+__device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned* p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_addr(p)), "r"(v) : "memory");
+    return old;
+}
+
+// the same on a shared-window address (saves the generic -> shared conversion in a hot loop)
+__device__ __forceinline__ void mbarrier_wait_sa(uint32_t bar_sa, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar_sa), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// The 3 bytes of a pixel that starts at byte (shift / 8) % 4 of the aligned shared-memory word at
+// word_sa + offset (+ one byte of garbage on top): two words and a funnel shift (SHF takes its
+// count modulo 32).
+__device__ __forceinline__ uint32_t lds_pixel(uint32_t word_sa, uint32_t offset, uint32_t shift) {
+    uint32_t lo, hi;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lo) : "r"(word_sa + offset));
+    asm volatile("ld.shared.b32 %0, [%1+4];" : "=r"(hi) : "r"(word_sa + offset));
+    return __funnelshift_r(lo, hi, shift);
+}
+
+__device__ __forceinline__ void sts32(uint32_t sa, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
+}
+
 // generic-proxy writes to shared memory -> visible to the async proxy (before a bulk store)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

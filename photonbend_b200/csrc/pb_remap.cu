@@ -347,7 +347,7 @@ constexpr int kMaxTiledSmem = 200 * 1024;
 
 template <int OUT_KIND, int SRC_KIND, int MODE>
 static cudaError_t launch_tiled_one(const TiledArgs& a, cudaStream_t st) {
-    const int smem = tiled_smem_bytes<SRC_KIND, MODE>(a.stage_pitch, a.stage_boxes, a.n_buffers, a.n_out);
+    const int smem = tiled_smem_bytes<SRC_KIND, MODE>(a.stage_bytes, a.n_buffers, a.n_out);
     static bool configured = false;  // per instantiation; the attribute is per device function
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE>,
@@ -392,8 +392,8 @@ struct pb_plan {
     pb::SrcGeom src;
     pb::Rotations rot;
     bool separable;      // un-rotated equirect output, camera / double source
-    int stage_pitch;     // bytes per staged source row (TMA box width)
-    int stage_boxes;     // 16-row TMA boxes per stage buffer
+    int stage_bytes;     // capacity of one stage buffer (a tile stages rows x its own row pitch)
+    int max_units;       // widest staged row of any tile, in 16-byte units (one tensor map per width)
     int raster_band;     // tile rows per raster band (see remap_tiled_kernel)
     double* tables;      // device: col_tab [W][2], row_tab [H][4], then the per-tile footprints; null unless separable
     int device;
@@ -423,8 +423,8 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     std::memcpy(p.rot.m, d.rotations, sizeof(p.rot.m));
     p.separable = d.out.kind == PB_KIND_EQUIRECT && d.n_rotations == 0 && d.src.kind != PB_KIND_EQUIRECT &&
                   d.channels == 3;
-    p.stage_pitch = 304;  // 101 source pixels; an odd number of 16-byte units (see pick_stage)
-    p.stage_boxes = 6;    // 96 source rows
+    p.stage_bytes = 24 * 1024;  // un-tuned default (pb_remap_u8 without a plan)
+    p.max_units = 19;           // rows of up to 304 bytes = 101 source pixels
     p.raster_band = 16;
     if (const char* e = std::getenv("PB_RASTER_BAND")) p.raster_band = std::atoi(e);  // tuning experiments
     p.tables = nullptr;
@@ -447,38 +447,37 @@ static const int4* footprint_table(const pb_plan& p, const double* tables) {
     return reinterpret_cast<const int4*>(tables + 2 * (size_t)p.out.W + 4 * (size_t)p.out.H);
 }
 
+// Picks the stage-buffer capacity from the census h (see kProbeSizeBins): the smallest size that
+// holds the footprint of all but 0.5 % of the (tile, slot) items -- the rest gather straight from
+// global memory -- so that the buffers are as small, and the occupancy as high, as the geometry
+// allows.  Staged rows are an odd number of 16-byte units wide (stage_units): vertically adjacent
+// source pixels then sit 4*odd banks apart (8 distinct bank groups) instead of piling onto 1-4 of
+// them, which is what the gather of a tile whose footprint runs down the source image would
+// otherwise do (tests/analysis/stage_sim.py: 4.4 -> 2.3 wavefronts per LDS at pitch 256 -> 272).
 static void pick_stage(pb_plan& p, const int* h) {
-    long long tiles = 0;
-    for (int k = 0; k < kProbePitchBins; ++k) tiles += h[k];
-    if (tiles <= 0) return;
-    const long long need = tiles - tiles / 200;  // all but 0.5 % of the tiles
+    long long items = 0;
+    for (int k = 0; k < kProbeSizeBins; ++k) items += h[k];
+    if (items <= 0) return;
+    const long long need = items - items / 200;
     long long acc = 0;
-    int pitch_bin = kProbePitchBins - 1, box_bin = kProbeBoxBins - 1;
-    for (int k = 0; k < kProbePitchBins; ++k) {
+    int kib = kProbeSizeBins - 1;
+    for (int k = 0; k < kProbeSizeBins; ++k) {
         acc += h[k];
-        if (acc >= need) { pitch_bin = k; break; }
+        if (acc >= need) { kib = k; break; }
     }
-    acc = 0;
-    for (int k = 0; k < kProbeBoxBins; ++k) {
-        acc += h[kProbePitchBins + k];
-        if (acc >= need) { box_bin = k; break; }
-    }
-    // An odd number of 16-byte units per staged row: vertically adjacent source pixels then sit
-    // 4*odd banks apart (8 distinct bank groups) instead of piling onto 1-4 of them, which is what
-    // the gather of a tile whose footprint runs down the source image would otherwise do
-    // (tests/analysis/stage_sim.py: 4.4 -> 2.3 wavefronts per LDS at pitch 256 -> 272).
-    int units = pitch_bin < 5 ? 5 : pitch_bin, boxes = box_bin < 1 ? 1 : box_bin;
-    if (units % 2 == 0 && !std::getenv("PB_PITCH_EVEN")) ++units;
-    if (units > 31) units = 31;  // u16 tensor map: at most 256 elements per box row
-    if (const char* e = std::getenv("PB_STAGE_UNITS")) units = std::atoi(e);  // tuning experiments
-    int pitch = 16 * units;
-    while (boxes > 1 && boxes * kBoxRows * pitch > 48 * 1024) --boxes;
-    p.stage_pitch = pitch;
-    p.stage_boxes = boxes;
+    if (kib < 2) kib = 2;
+    if (kib > 48) kib = 48;
+    if (const char* e = std::getenv("PB_STAGE_KIB")) kib = std::atoi(e);  // tuning experiments
+    p.stage_bytes = kib * 1024;
+    int units = h[kProbeSizeBins];
+    if (units < kMinStageUnits) units = kMinStageUnits;
+    if (units > kMaxStageUnits) units = kMaxStageUnits;
+    p.max_units = units | 1;
 }
 
 static void tune_stage(pb_plan& p, cudaStream_t st) {
     if (p.desc.channels != 3) return;
+    int h[kProbeInts] = {0};
     if (p.separable && p.tables) {
         // the per-tile footprints are already on the device: histogram them on the host
         const int n_entries = footprint_entries(p);
@@ -486,12 +485,15 @@ static void tune_stage(pb_plan& p, cudaStream_t st) {
         if (!host) return;
         if (cudaMemcpyAsync(host, footprint_table(p, p.tables), sizeof(int4) * n_entries, cudaMemcpyDeviceToHost, st) ==
                 cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess) {
-            int h[kProbePitchBins + kProbeBoxBins] = {0};
             for (int e = 0; e < n_entries; ++e) {
                 if (host[e].z == 0) continue;
-                const int pb = ((host[e].w >> 1) + 15) / 16, bb = host[e].z;
-                h[pb < kProbePitchBins - 1 ? pb : kProbePitchBins - 1] += 1;
-                h[kProbePitchBins + (bb < kProbeBoxBins - 1 ? bb : kProbeBoxBins - 1)] += 1;
+                const int units = stage_units(host[e].w >> 1);
+                const int bytes = host[e].z * kBoxRows * 16 * units;
+                const bool fits = units <= kMaxStageUnits;
+                int bin = (bytes + 1023) >> 10;
+                if (!fits || bin > kProbeSizeBins - 1) bin = kProbeSizeBins - 1;
+                h[bin] += 1;
+                if (fits && units > h[kProbeSizeBins]) h[kProbeSizeBins] = units;
             }
             pick_stage(p, h);
         } else {
@@ -501,12 +503,11 @@ static void tune_stage(pb_plan& p, cudaStream_t st) {
         return;
     }
     int* census = nullptr;
-    const int n = kProbePitchBins + kProbeBoxBins;
-    if (cudaMalloc((void**)&census, n * sizeof(int)) != cudaSuccess) {
+    if (cudaMalloc((void**)&census, sizeof(h)) != cudaSuccess) {
         (void)cudaGetLastError();
         return;
     }
-    cudaMemsetAsync(census, 0, n * sizeof(int), st);
+    cudaMemsetAsync(census, 0, sizeof(h), st);
     TiledArgs a;
     std::memset(&a, 0, sizeof(a));
     a.out = p.out;
@@ -516,15 +517,14 @@ static void tune_stage(pb_plan& p, cudaStream_t st) {
     a.row_tab = p.tables ? p.tables + 2 * (size_t)p.out.W : nullptr;
     a.n_frames = 0;
     a.src_pitch = p.src.W * 3;
-    a.stage_pitch = 512;
-    a.stage_boxes = 1;
+    a.stage_bytes = 256;
+    a.max_units = kMaxStageUnits;
     a.n_buffers = 1;
     a.n_out = 1;
     a.probe = census;
     a.tiles_x = tiles_x(p);
     a.tiles_y = tiles_y(p);
     a.raster_band = 0;
-    int h[kProbePitchBins + kProbeBoxBins];
     if (launch_tiled(a, p.separable && p.tables != nullptr, st) == cudaSuccess &&
         cudaMemcpyAsync(h, census, sizeof(h), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
         cudaStreamSynchronize(st) == cudaSuccess) {
@@ -582,10 +582,13 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         // L2 traffic (cfg5: 543 -> 500 Gpix/s), so it gets none  (gpurun_out/run3.log)
         a.l2_ahead = (p.src.kind == PB_KIND_DOUBLE) ? 0 : 2;
         if (const char* e = std::getenv("PB_L2_AHEAD")) a.l2_ahead = std::atoi(e);  // tuning experiments
-        // stage geometry: one column of 16-row TMA boxes per slot
+#ifdef PB_EXPERIMENTS
+        if (const char* e = std::getenv("PB_DEBUG_MODE")) a.debug = std::atoi(e);
+#endif
+        // stage geometry: one column of 16-row TMA boxes per slot, as wide as the tile needs
         const bool dbl = p.src.kind == PB_KIND_DOUBLE;
-        a.stage_pitch = p.stage_pitch;
-        a.stage_boxes = p.stage_boxes;
+        a.stage_bytes = p.stage_bytes;
+        a.max_units = p.max_units;
         // a second stage buffer lets the loads of the next (frame, slot) item overlap the current
         // gather; taken when three CTAs per SM still fit
         a.n_out = multi ? 2 : 1;
@@ -593,14 +596,17 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         if (multi || dbl) {
             const int mode = (p.separable && tables != nullptr) ? 1 : 0;
             int two;
-            if (dbl) two = mode ? tiled_smem_bytes<PB_KIND_DOUBLE, 1>(a.stage_pitch, a.stage_boxes, 2, a.n_out)
-                                : tiled_smem_bytes<PB_KIND_DOUBLE, 0>(a.stage_pitch, a.stage_boxes, 2, a.n_out);
-            else two = mode ? tiled_smem_bytes<PB_KIND_CAMERA, 1>(a.stage_pitch, a.stage_boxes, 2, a.n_out)
-                            : tiled_smem_bytes<PB_KIND_CAMERA, 0>(a.stage_pitch, a.stage_boxes, 2, a.n_out);
+            if (dbl) two = mode ? tiled_smem_bytes<PB_KIND_DOUBLE, 1>(a.stage_bytes, 2, a.n_out)
+                                : tiled_smem_bytes<PB_KIND_DOUBLE, 0>(a.stage_bytes, 2, a.n_out);
+            else two = mode ? tiled_smem_bytes<PB_KIND_CAMERA, 1>(a.stage_bytes, 2, a.n_out)
+                            : tiled_smem_bytes<PB_KIND_CAMERA, 0>(a.stage_bytes, 2, a.n_out);
             if (two <= 75 * 1024) a.n_buffers = 2;
         }
-        if (encode_frames_map(&a.src_map, src, src_pitch, p.src.H, n_frames, src_frame_stride, 2, a.stage_pitch,
-                              kBoxRows) &&
+        bool maps_ok = true;
+        for (int u = kMinStageUnits; u <= a.max_units && maps_ok; u += 2)
+            maps_ok = encode_frames_map(&a.src_maps[(u - kMinStageUnits) / 2], src, src_pitch, p.src.H, n_frames,
+                                        src_frame_stride, 2, 16 * u, kBoxRows);
+        if (maps_ok &&
             encode_frames_map(&a.dst_map, dst, dst_pitch, p.out.H, n_frames, dst_frame_stride, 1, kOutRowBytes,
                               kTileH)) {
             cudaError_t e = launch_tiled(a, p.separable && tables != nullptr, st);
