@@ -129,8 +129,10 @@ __global__ void __launch_bounds__(256) pb_tables_kernel(const __grid_constant__ 
     }
 }
 
+constexpr int kMaxGroups = 8;  // frames in flight per tile (lean loop)
+
 struct alignas(16) TileShared {
-    uint64_t bar[2];  // one mbarrier per stage buffer
+    uint64_t bar[kMaxGroups];  // one mbarrier per stage buffer (general loop) / frame group (lean loop)
     int min_x[2], max_x[2], min_y[2], max_y[2];
 };
 
@@ -411,8 +413,8 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 
     if (tid == 0) {
         if (a.probe == nullptr) ptx::prefetch_tensormap(&a.dst_map);
-        ptx::mbarrier_init(&sh->bar[0], 1);
-        ptx::mbarrier_init(&sh->bar[1], 1);
+#pragma unroll
+        for (int g = 0; g < kMaxGroups; ++g) ptx::mbarrier_init(&sh->bar[g], 1);
         ptx::fence_mbarrier_init();
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -422,8 +424,10 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             sh->max_y[s] = -1;
         }
     }
-    if (tid < a.n_buffers * 8)
+    if (tid < a.n_buffers * 8) {
         reinterpret_cast<int4*>(stages + (tid >> 3) * buf_bytes + ztail)[tid & 7] = make_int4(0, 0, 0, 0);
+        ptx::fence_async_smem();  // (the lean loop lays the stage area out differently: TMA may write here)
+    }
 
     // ---------------------------------------------------------------- 1. resolve (generic)  2. footprint
     // separable: start the table loads now, they are consumed after the barrier
@@ -568,7 +572,50 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 #else
     constexpr bool dbg_noload = false, dbg_nogather = false, dbg_nostore = false;
 #endif
-    if (tid == 0 && !dbg_noload) {
+    // The common case -- no weighted blend anywhere in the tile -- runs the lean frame loop further
+    // down.  It treats the stage area as a ring of frame groups: [128 zero bytes][slot 0 rectangle]
+    // [slot 1 rectangle], as many as fit, each with its own mbarrier, so that a tile with a small
+    // footprint keeps more frames in flight than one with a large footprint.
+    const int rect0 = nbox[0] * kBoxRows * pitch[0];
+    const int rect1 = (NSLOT == 2) ? nbox[S1] * kBoxRows * pitch[S1] : 0;
+    const int group_bytes = 128 + rect0 + rect1;
+    int n_groups = min(min(kMaxGroups, a.n_frames), (a.n_buffers * buf_bytes) / group_bytes);
+#ifdef PB_EXPERIMENTS
+    if (a.debug >> 8) n_groups = min(n_groups, a.debug >> 8);
+#endif
+    const bool lean = unit_weights && n_act >= 1 && n_groups >= min(2, a.n_frames) &&
+                      (a.n_out == 2 || a.n_frames == 1) && !dbg_noload && !dbg_nogather && !dbg_nostore;
+    auto issue_group = [&](int f, int g) {  // one thread: every rectangle of frame f into group g
+        unsigned char* base = stages + g * group_bytes + 128;
+        ptx::mbarrier_arrive_expect_tx(&sh->bar[g], (unsigned)(rect0 + rect1));
+        const uint64_t keep = ptx::policy_evict_last();
+        if (nbox[0] > 0) {
+            const CUtensorMap* map = &a.src_maps[(pitch[0] >> 5) - (kMinStageUnits >> 1)];
+            for (int k = 0; k < nbox[0]; ++k)
+                ptx::tma_load_3d_hint(base + k * kBoxRows * pitch[0], map, xb0[0] >> 1, by0[0] + k * kBoxRows, f, &sh->bar[g],
+                                      keep);
+        }
+        if (NSLOT == 2 && nbox[S1] > 0) {
+            const CUtensorMap* map = &a.src_maps[(pitch[S1] >> 5) - (kMinStageUnits >> 1)];
+            for (int k = 0; k < nbox[S1]; ++k)
+                ptx::tma_load_3d_hint(base + rect0 + k * kBoxRows * pitch[S1], map, xb0[S1] >> 1, by0[S1] + k * kBoxRows, f,
+                                      &sh->bar[g], keep);
+        }
+    };
+    auto prefetch_group = [&](int f) {  // one thread: frame f into L2
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            const CUtensorMap* map = &a.src_maps[(pitch[s] >> 5) - (kMinStageUnits >> 1)];
+            for (int k = 0; k < nbox[s]; ++k) ptx::tma_prefetch_l2_3d(map, xb0[s] >> 1, by0[s] + k * kBoxRows, f);
+        }
+    };
+    if (lean) {
+        if (tid < n_groups * 8) reinterpret_cast<int4*>(stages + (tid >> 3) * group_bytes)[tid & 7] = make_int4(0, 0, 0, 0);
+        if (tid == 0) {
+            for (int f = 0; f < n_groups; ++f) issue_group(f, f);
+            for (int f = n_groups; f < min(n_groups + a.l2_ahead, a.n_frames); ++f) prefetch_group(f);
+        }
+    } else if (tid == 0 && !dbg_noload) {
         for (int t = 0; t < min(a.n_buffers, n_items); ++t) issue_item(t);
         for (int t = a.n_buffers; t < min(a.n_buffers + a.l2_ahead, n_items); ++t) prefetch_item(t);
     }
@@ -622,115 +669,69 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         }
     }
 
-    // ---------------------------------------------------------------- 4. gather  5. store (lean loops)
-    // The common case -- two stage buffers, no weighted blend anywhere in the tile -- runs a frame
-    // loop with everything hoisted: per pixel two LDS and one funnel shift, per frame one block
-    // barrier per active slot.  Thread 0 feeds the TMA queue right after each barrier.
+    // ---------------------------------------------------------------- 4. gather  5. store (lean loop)
+    // Everything is hoisted: per pixel and slot two LDS and one funnel shift, per frame one block
+    // barrier; thread 0 refills the group and stores the tile right after it.
     const unsigned stages_sa = ptx::smem_addr(stages);
-    if (a.n_buffers == 2 && (a.n_out == 2 || a.n_frames == 1) && unit_weights && n_act >= 1 && !dbg_noload && !dbg_nogather && !dbg_nostore) {
-        const uint64_t keep = ptx::policy_evict_last(), drop = ptx::policy_evict_first();
+    if (lean) {
+        const uint64_t drop = ptx::policy_evict_first();
         const unsigned out_sa = ptx::smem_addr(out_tiles) + rg * kOutRowBytes + qc * 12;
         const unsigned out_flip = (a.n_out == 2) ? kOutTileBytes : 0;
         const unsigned bar_sa = ptx::smem_addr(&sh->bar[0]);
-        if (n_act == 1) {
-            // one source rectangle per frame: frame f sits in buffer f & 1
-            const int s1 = first;
-            const int r_by0 = by0[s1], r_x = xb0[s1] >> 1, r_nbox = nbox[s1], r_box = kBoxRows * pitch[s1];
-            const CUtensorMap* map = &a.src_maps[(pitch[s1] >> 5) - (kMinStageUnits >> 1)];
-            unsigned adr[kPxPerThread], shf[kPxPerThread];
+        // loc -> address inside a group (pixels without a source read the group's zero bytes)
+        unsigned adr[NSLOT][kPxPerThread], shf[NSLOT][kPxPerThread];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s)
 #pragma unroll
             for (int p = 0; p < kPxPerThread; ++p) {
-                const int l = (NSLOT == 2 && s1) ? loc[S1][p] : loc[0][p];
-                adr[p] = stages_sa + (unsigned)(l & ~3);
-                shf[p] = (unsigned)l << 3;
+                const int l = loc[s][p];
+                const int rel = (l == ztail) ? 0 : l + 128 + (s ? rect0 : 0);
+                adr[s][p] = stages_sa + (unsigned)(rel & ~3);
+                shf[s][p] = (unsigned)rel << 3;
             }
-            // (frames in pairs, so that the buffer a frame uses is a compile-time constant)
-            auto one_frame = [&](int f, auto B) {
-                constexpr unsigned b = decltype(B)::value;
-                ptx::mbarrier_wait_sa(bar_sa + 8 * b, (unsigned)(f >> 1) & 1u);
+        __syncthreads();  // the groups' zero bytes are in place
+        auto frame_loop = [&](auto ACT) {
+            constexpr int act = decltype(ACT)::value;  // 1: slot 0 only, 2: slot 1 only, 3: both
+            int g = 0;
+            unsigned parity = 0;
+            for (int f = 0; f < a.n_frames; ++f) {
+                const unsigned goff = (unsigned)(g * group_bytes);
+                ptx::mbarrier_wait_sa(bar_sa + 8 * g, parity);
                 unsigned v[kPxPerThread];
+                if (act & 1) {
 #pragma unroll
-                for (int p = 0; p < kPxPerThread; ++p) v[p] = ptx::lds_pixel(adr[p], b * buf_bytes, shf[p]);
-                const unsigned o = out_sa + b * out_flip;
+                    for (int p = 0; p < kPxPerThread; ++p) v[p] = ptx::lds_pixel(adr[0][p], goff, shf[0][p]);
+                }
+                if (act & 2) {
+#pragma unroll
+                    for (int p = 0; p < kPxPerThread; ++p) {
+                        const unsigned w = ptx::lds_pixel(adr[S1][p], goff, shf[S1][p]);
+                        v[p] = (act & 1) ? __vadd4(v[p], w) : w;
+                    }
+                }
+                const unsigned o = out_sa + (f & 1) * out_flip;
 #pragma unroll
                 for (int q = 0; q < kRowsPerThread; ++q) store_quad_sa(o + q * kRowGroups * kOutRowBytes, v + q * 4);
                 ptx::fence_async_smem();
                 if (tid == 0) ptx::bulk_wait_read0();  // stores up to frame f - 1 have left their tiles
                 __syncthreads();
                 if (tid == 0) {
-                    if (f + 2 < a.n_frames) {
-                        ptx::mbarrier_arrive_expect_tx(&sh->bar[b], (unsigned)(r_nbox * r_box));
-                        for (int k = 0; k < r_nbox; ++k)
-                            ptx::tma_load_3d_hint(stages + b * buf_bytes + k * r_box, map, r_x, r_by0 + k * kBoxRows, f + 2,
-                                                  &sh->bar[b], keep);
-                    }
-                    ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, y0, f, out_tiles + b * out_flip, drop);
+                    if (f + n_groups < a.n_frames) issue_group(f + n_groups, g);
+                    ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, y0, f, out_tiles + (f & 1) * out_flip, drop);
                     ptx::bulk_commit();
-                    if (a.l2_ahead > 0 && f + 2 + a.l2_ahead < a.n_frames)
-                        for (int k = 0; k < r_nbox; ++k)
-                            ptx::tma_prefetch_l2_3d(map, r_x, r_by0 + k * kBoxRows, f + 2 + a.l2_ahead);
+                    if (a.l2_ahead > 0 && f + n_groups + a.l2_ahead < a.n_frames) prefetch_group(f + n_groups + a.l2_ahead);
                 }
-            };
-            for (int f = 0; f < a.n_frames; f += 2) {
-                one_frame(f, std::integral_constant<unsigned, 0>{});
-                if (f + 1 < a.n_frames) one_frame(f + 1, std::integral_constant<unsigned, 1>{});
-            }
-            if (tid == 0) ptx::bulk_wait_read0();
-            return;
-        }
-        if (NSLOT == 2) {
-            // two rectangles per frame: slot 0 of every frame goes through buffer 0, slot 1 through buffer 1
-            const int r_box0 = kBoxRows * pitch[0], r_box1 = kBoxRows * pitch[S1];
-            const CUtensorMap* map0 = &a.src_maps[(pitch[0] >> 5) - (kMinStageUnits >> 1)];
-            const CUtensorMap* map1 = &a.src_maps[(pitch[S1] >> 5) - (kMinStageUnits >> 1)];
-            unsigned adr0[kPxPerThread], shf0[kPxPerThread], adr1[kPxPerThread], shf1[kPxPerThread];
-#pragma unroll
-            for (int p = 0; p < kPxPerThread; ++p) {
-                adr0[p] = stages_sa + (unsigned)(loc[0][p] & ~3);
-                shf0[p] = (unsigned)loc[0][p] << 3;
-                adr1[p] = stages_sa + buf_bytes + (unsigned)(loc[S1][p] & ~3);
-                shf1[p] = (unsigned)loc[S1][p] << 3;
-            }
-            auto two_frame = [&](int f, auto P) {
-                constexpr unsigned par = decltype(P)::value;
-                ptx::mbarrier_wait_sa(bar_sa, par);
-                unsigned v[kPxPerThread];
-#pragma unroll
-                for (int p = 0; p < kPxPerThread; ++p) v[p] = ptx::lds_pixel(adr0[p], 0, shf0[p]);
-                if (tid == 0) ptx::bulk_wait_read1();  // the store of frame f - 2 has left its tile
-                __syncthreads();
-                if (tid == 0 && f + 1 < a.n_frames) {
-                    ptx::mbarrier_arrive_expect_tx(&sh->bar[0], (unsigned)(nbox[0] * r_box0));
-                    for (int k = 0; k < nbox[0]; ++k)
-                        ptx::tma_load_3d_hint(stages + k * r_box0, map0, xb0[0] >> 1, by0[0] + k * kBoxRows, f + 1, &sh->bar[0],
-                                              keep);
+                if (++g == n_groups) {
+                    g = 0;
+                    parity ^= 1u;
                 }
-                ptx::mbarrier_wait_sa(bar_sa + 8, par);
-#pragma unroll
-                for (int p = 0; p < kPxPerThread; ++p) v[p] = __vadd4(v[p], ptx::lds_pixel(adr1[p], 0, shf1[p]));
-                const unsigned o = out_sa + par * out_flip;
-#pragma unroll
-                for (int q = 0; q < kRowsPerThread; ++q) store_quad_sa(o + q * kRowGroups * kOutRowBytes, v + q * 4);
-                ptx::fence_async_smem();
-                __syncthreads();
-                if (tid == 0) {
-                    if (f + 1 < a.n_frames) {
-                        ptx::mbarrier_arrive_expect_tx(&sh->bar[1], (unsigned)(nbox[S1] * r_box1));
-                        for (int k = 0; k < nbox[S1]; ++k)
-                            ptx::tma_load_3d_hint(stages + buf_bytes + k * r_box1, map1, xb0[S1] >> 1, by0[S1] + k * kBoxRows,
-                                                  f + 1, &sh->bar[1], keep);
-                    }
-                    ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, y0, f, out_tiles + par * out_flip, drop);
-                    ptx::bulk_commit();
-                }
-            };
-            for (int f = 0; f < a.n_frames; f += 2) {
-                two_frame(f, std::integral_constant<unsigned, 0>{});
-                if (f + 1 < a.n_frames) two_frame(f + 1, std::integral_constant<unsigned, 1>{});
             }
-            if (tid == 0) ptx::bulk_wait_read0();
-            return;
-        }
+        };
+        if (n_act == 2) frame_loop(std::integral_constant<int, 3>{});
+        else if (first == 0) frame_loop(std::integral_constant<int, 1>{});
+        else frame_loop(std::integral_constant<int, 2>{});
+        if (tid == 0) ptx::bulk_wait_read0();
+        return;
     }
 
     // ---------------------------------------------------------------- 4. gather  5. store (general loop)
