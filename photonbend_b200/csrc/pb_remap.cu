@@ -577,10 +577,10 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         a.tiles_x = tiles_x(p);
         a.tiles_y = tiles_y(p);
         a.raster_band = p.raster_band;
-        // L2 prefetch of the items two ahead: +7 % on a single-lens source (T: 1014 -> 1091 Gpix/s);
-        // a double source already keeps two items per frame in flight and loses 8 % to the extra
-        // L2 traffic (cfg5: 543 -> 500 Gpix/s), so it gets none  (gpurun_out/run3.log)
-        a.l2_ahead = (p.src.kind == PB_KIND_DOUBLE) ? 0 : 2;
+        // L2 prefetch (UTMAPF) of frames beyond those in flight: worth +7 % on a single-lens source
+        // while tiles kept two frames in flight; with the ring of frame groups it is neutral
+        // (8K target) or harmful (double source, -8 %), so it is off  (gpurun_out/run3.log, run12.log)
+        a.l2_ahead = 0;
         if (const char* e = std::getenv("PB_L2_AHEAD")) a.l2_ahead = std::atoi(e);  // tuning experiments
 #ifdef PB_EXPERIMENTS
         if (const char* e = std::getenv("PB_DEBUG_MODE")) a.debug = std::atoi(e);

@@ -583,7 +583,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 #ifdef PB_EXPERIMENTS
     if (a.debug >> 8) n_groups = min(n_groups, a.debug >> 8);
 #endif
-    const bool lean = unit_weights && n_act >= 1 && n_groups >= min(2, a.n_frames) &&
+    const bool lean = unit_weights && n_act >= 1 && n_groups >= 1 &&
                       (a.n_out == 2 || a.n_frames == 1) && !dbg_noload && !dbg_nogather && !dbg_nostore;
     auto issue_group = [&](int f, int g) {  // one thread: every rectangle of frame f into group g
         unsigned char* base = stages + g * group_bytes + 128;
