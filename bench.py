@@ -61,6 +61,27 @@ def algorithmic_bytes_per_frame(name: str) -> int:
     return CHANNELS * (info["out_pixels"] + info["n_touched"])
 
 
+def committed_traffic(name: str, frames: int):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)."""
+    path = os.path.join(REPO, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        entry = json.load(fh).get(f"{name}:{frames}")
+    return entry["bytes"] if entry else None
+
+
+def bench_config(name: str, frames: int) -> dict:
+    """The workload both arms (--impl b200 / reference) are quoted on."""
+    wl = workloads.WORKLOADS[name]
+    info = golden_info(name)
+    return {"workload": name, "title": wl["title"], "frames_per_step_per_gpu": frames,
+            "out": f"{info['shape'][1]}x{info['shape'][0]}x{CHANNELS} u8",
+            "l2": "inputs larger than L2: each step reads and writes "
+                  f"{frames} distinct frames ({frames * (info['src_pixels'] + info['out_pixels']) * 3 / 1e6:.0f} MB)",
+            "sharding": "frames k mod N per GPU, no collective"}
+
+
 def measured_peak_gbs():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -89,7 +110,7 @@ def _cpu_band_worker(args):
 _CPU_IMAGE = [None]
 
 
-def cpu_reference_pass(name: str, procs: int, row_fraction: float):
+def cpu_reference_pass(name: str, procs: int, row_fraction: float, repeat: int = 1):
     """One bounded pass of the NumPy port: the first ``row_fraction`` of the output rows of one
     frame, split into ``procs`` row bands run by ``procs`` processes (the reference's protocol
     works on any row band of the map, bit-identically).  Returns (pixels, seconds)."""
@@ -108,6 +129,7 @@ def cpu_reference_pass(name: str, procs: int, row_fraction: float):
     for k in range(n_bands):
         r0 = min(h - band_rows, int(k * stride))
         bands.append((name, r0, r0 + band_rows))
+    bands = bands * max(1, repeat)  # more than one frame's worth of rows: the same frame again
     chunks = 1
     _CPU_IMAGE[0] = workloads.source_image(wl)
     ctx = mp.get_context("fork")
@@ -125,16 +147,18 @@ def cpu_baseline(name: str, budget_s: float = 20.0):
     rate = px / dt
     h = workloads.WORKLOADS[name]["out"]["height"]
     w = workloads.output_shape(workloads.WORKLOADS[name]["out"])[1]
-    frac = min(1.0, max(0.01, rate * budget_s / (h * w)))
-    px, dt = cpu_reference_pass(name, procs, frac)
+    frames_worth = rate * budget_s / (h * w)
+    frac = min(1.0, max(0.01, frames_worth))
+    repeat = max(1, min(64, int(round(frames_worth)))) if frames_worth > 1.0 else 1
+    px, dt = cpu_reference_pass(name, procs, frac, repeat)
     return {
         "value": px / dt / 1e9,
         "unit": UNIT,
         "cores": procs,
         "kind": "port",
         "sample": f"oracle/numpy_port.py (NumPy restatement, bit-identical to the reference), "
-                  f"{procs} processes over {px // w} of {h} output rows of one {name} frame "
-                  f"(64-row bands spread evenly over the frame), {dt:.1f} s wall",
+                  f"{procs} processes over {px // w} output rows ({px / (h * w):.2f} frames of {h} rows) of {name} "
+                  f"(64-row bands spread evenly over the frame), {dt:.1f} s wall = {dt * procs:.0f} core-seconds",
     }
 
 
@@ -381,7 +405,8 @@ def run_gpu(args):
     achieved = algorithmic_bytes_per_frame(name) * frames / (avg_launch_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": args.traffic_bytes, "peak_source": peak_src,
+        "traffic": args.traffic_bytes if args.traffic_bytes is not None else committed_traffic(name, frames),
+        "traffic_source": "ncu --set full capture of one launch, profiles/traffic.json", "peak_source": peak_src,
         "kernel": "pb::remap kernel (one launch per step)", "launch_ms": avg_launch_ms,
         "algorithmic_bytes_per_launch": algorithmic_bytes_per_frame(name) * frames,
     }
@@ -398,11 +423,7 @@ def run_gpu(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 index math, u8 pixels",
             "data": "synthetic uniform-noise uint8 frames (seeded), generated on device",
-            "config": {"workload": name, "title": wl["title"], "frames_per_step_per_gpu": frames,
-                       "out": f"{info['shape'][1]}x{info['shape'][0]}x{CHANNELS} u8",
-                       "l2": "inputs larger than L2: each step reads and writes "
-                             f"{frames} distinct frames ({frames * (info['src_pixels'] + info['out_pixels']) * 3 / 1e6:.0f} MB)",
-                       "sharding": "frames k mod N per GPU, no collective"},
+            "config": bench_config(name, frames),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "photonbend_b200.batch.FramePipeline (pinned host frames in and out, depth 3)",
                     "steps": max(1, args.e2e_steps)},
@@ -435,23 +456,26 @@ def run_reference(args):
     h = wl["out"]["height"]
     w = workloads.output_shape(wl["out"])[1]
     per_step_s = max(1.0, args.cpu_budget * 6 / (args.steps + args.warmup))
-    frac = min(1.0, max(0.005, rate * per_step_s / (h * w)))
+    frames_worth = rate * per_step_s / (h * w)
+    frac = min(1.0, max(0.005, frames_worth))
+    repeat = max(1, min(64, int(round(frames_worth)))) if frames_worth > 1.0 else 1
     for _ in range(args.warmup):
-        cpu_reference_pass(name, procs, frac)
+        cpu_reference_pass(name, procs, frac, repeat)
     tot_px, tot_dt = 0, 0.0
     for _ in range(args.steps):
-        px, dt = cpu_reference_pass(name, procs, frac)
+        px, dt = cpu_reference_pass(name, procs, frac, repeat)
         tot_px += px
         tot_dt += dt
     value = tot_px / tot_dt / 1e9
     sample = (f"oracle/numpy_port.py (NumPy restatement of the reference, bit-identical), {procs} processes, "
-              f"each step = {px // w} of {h} output rows of one {name} frame (64-row bands spread evenly)")
+              f"each step = {px // w} output rows ({px / (h * w):.2f} frames of {h} rows) of {name} "
+              f"(64-row bands spread evenly), {tot_dt / args.steps:.1f} s wall per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot_dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 index math, u8 pixels", "data": "synthetic uniform-noise uint8 frame (seeded)",
-        "config": {"workload": name, "title": wl["title"]},
+        "config": bench_config(name, args.frames),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
