@@ -1,0 +1,249 @@
+// pb_fast.cuh -- guarded short cut through the per-pixel float64 chain (sm_100a).
+//
+// The exact chain (pb_device.cuh: output_ray -> rotate_ray* -> source_lookup) follows the
+// reference call by call: every rotation goes latitude/longitude -> unit vector -> matrix ->
+// acos/atan2 -> latitude/longitude again (rotation.py:129-164), and every projection goes through
+// its angle (projection.py:189-193, 251-252).  That is seven libm calls per pixel for a rotated
+// camera -> camera remap and ~760 instructions; the FP64 pipe, not HBM, bounds such a launch.
+//
+// The short cut keeps the ray as a unit vector from the output pixel to the source projection:
+//   * lens inverses that are algebraic in the radius give (sin lat, cos lat) without asin/atan
+//     (equisolid, orthographic, stereographic, rectilinear), and cos/sin of the pixel's longitude
+//     are x/r, y/r;
+//   * rotations are plain matrix products of the vector;
+//   * lens forwards that are algebraic in cos(lat) need no angle either; an equidistant source
+//     needs one acos, a panorama source one acos + one atan2.
+// It evaluates the same real function as the exact chain, but rounds differently (~1e-15
+// relative), so its truncated source index can differ where a coordinate sits within ~1e-9 px of
+// an integer.  Therefore every decision the short cut takes -- each truncation, the fov test, the
+// lens domains, the blend band of a double source -- is only accepted when the value is further
+// than a guard band from the decision boundary (eps = 1e-6 px, 1e-9 relative for angles; the two
+// chains differ by < 1e-8 px wherever the conditioning guards below let the short cut run).
+// Otherwise the pixel is "undecided" and the caller runs the exact chain for it (~4e-6 of the
+// pixels).  Results are therefore those of the exact chain, bit for bit
+// (tests/test_gpu_parity.py::test_fast_path_equals_exact_chain).
+#pragma once
+
+#include "pb_device.cuh"
+
+namespace pb {
+
+struct FastGeom {
+    int enabled;
+    int n_rot;
+    double eps;                    // guard band around integer source coordinates, pixels
+    // output side (camera / double)
+    double inv_f;                  // 1 / out.f
+    double r2_valid, r2_invalid;   // r^2 < r2_valid: inside the fov; r^2 > r2_invalid: outside; else undecided
+    double r2_domain;              // r^2 >= r2_domain: lens inverse near the edge of its domain -> undecided
+    // source side
+    double src_f;
+    double inv_seg_h, inv_seg_w;   // equirect source: rows / columns per radian
+    double ny_rect_in, ny_rect_out;  // rectilinear source lens: cos(lat) > in: tan defined; < out: NaN (no pixel)
+    double ny_band_lo, ny_band_hi;   // double source: cos(lat) in [lo, hi] may be blended -> undecided
+};
+
+constexpr double kTwo52 = 4503599627370496.0;
+
+// Index of source coordinate v along an axis of n pixels, under the reference's rule (truncate
+// toward zero, then 0 <= index < n; projection.py:223-231, 254-259):
+// >= 0 the index, -1 outside the image, -2 undecided (within eps of an integer, or not finite).
+__device__ __forceinline__ int fast_index(double v, int n, double eps) {
+    const double av = fabs(v);
+    const double nearest = __dadd_rn(__dadd_rn(av, kTwo52), -kTwo52);
+    const double dist = fabs(__dadd_rn(av, -nearest));
+    if (!(dist > eps) || !(av < 2147483648.0)) return -2;
+    const int idx = __double2loint(__dadd_rz(av, kTwo52));
+    return (v > -1.0 && v < (double)n) ? idx : -1;
+}
+
+// Unit vector of the ray of output pixel (i, j) before any rotation:
+// (cos lon sin lat, cos lat, sin lon sin lat), rotation.py:129-132.
+// 0 = ray inside the fov, 1 = outside (black pixel), 2 = undecided.
+template <int OUT_KIND>
+__device__ __forceinline__ int fast_out_vector(const OutGeom& g, const FastGeom& fg, int i, int j, double& vx,
+                                               double& vy, double& vz) {
+    if (OUT_KIND == PB_KIND_EQUIRECT) {
+        const double lon = linspace_at(g.x_start, g.x_stop, g.x_step, g.W, j);
+        const double lat = linspace_at(g.y_start, g.y_stop, g.y_step, g.H, i);
+        double sl, cl, so, co;
+        sincos(lat, &sl, &cl);
+        sincos(lon, &so, &co);
+        vx = co * sl;
+        vy = cl;
+        vz = so * sl;
+        return 0;
+    }
+    const bool right = (OUT_KIND == PB_KIND_DOUBLE) && j >= g.half_w;
+    const int n_cols = (OUT_KIND == PB_KIND_DOUBLE) ? g.half_w : g.W;
+    double x = linspace_at(g.x_start, g.x_stop, g.x_step, n_cols, right ? j - g.half_w : j);
+    if (right) x = -x;
+    const double y = linspace_at(g.y_start, g.y_stop, g.y_step, g.H, i);
+    const double r2 = fma(x, x, y * y);
+    if (!(r2 < fg.r2_domain)) return 2;
+    if (!(r2 < fg.r2_valid)) return (r2 > fg.r2_invalid) ? 1 : 2;
+    const double inv_f = fg.inv_f;
+    double k;  // sin(lat) / r
+    switch (g.lens) {
+        case PB_LENS_EQUISOLID: {  // sin(lat/2) = d/2
+            const double u2 = r2 * (0.25 * inv_f * inv_f);
+            k = sqrt(1.0 - u2) * inv_f;
+            vy = fma(-2.0, u2, 1.0);
+            break;
+        }
+        case PB_LENS_ORTHOGRAPHIC: {  // sin(lat) = d
+            k = inv_f;
+            vy = sqrt(fma(-r2, inv_f * inv_f, 1.0));
+            break;
+        }
+        case PB_LENS_STEREOGRAPHIC: {  // tan(lat/2) = d/2
+            const double t2 = r2 * (0.25 * inv_f * inv_f);
+            const double w = 1.0 / (1.0 + t2);
+            k = inv_f * w;
+            vy = (1.0 - t2) * w;
+            break;
+        }
+        case PB_LENS_RECTILINEAR: {  // tan(lat) = d
+            const double s = rsqrt(fma(r2, inv_f * inv_f, 1.0));
+            k = inv_f * s;
+            vy = s;
+            break;
+        }
+        default: {  // equidistant, thoby: the latitude itself is needed
+            if (!(r2 > 0.0)) return 2;
+            const double inv_r = rsqrt(r2);
+            const double d = r2 * inv_r * inv_f;
+            const double lat = (g.lens == PB_LENS_EQUIDISTANT) ? d : asin(d / 1.47) / 0.713;
+            double sl, cl;
+            sincos(lat, &sl, &cl);
+            k = sl * inv_r;
+            vy = cl;
+            break;
+        }
+    }
+    vx = x * k;
+    vz = y * k;
+    if (right) vy = -vy;  // lat = pi - lat (projection.py:381-382)
+    return 0;
+}
+
+// dist / sin(lat) of a camera source lens for a ray with cos(lat) = ny, sin(lat) = sqrt(h2),
+// dist = lens_forward(lat) * f (projection.py:251).  0 = ok, 1 = no pixel (NaN radius), 2 = undecided.
+__device__ __forceinline__ int fast_lens_q(int lens, const FastGeom& fg, double ny, double inv_h, double theta, double& q) {
+    const double f = fg.src_f;
+    switch (lens) {
+        case PB_LENS_EQUIDISTANT: q = theta * f * inv_h; return 0;
+        case PB_LENS_EQUISOLID:  // 2 sin(t/2) / sin t = 1 / cos(t/2)
+            if (!(1.0 + ny > 1e-8)) return 2;
+            q = f * rsqrt(0.5 * (1.0 + ny));
+            return 0;
+        case PB_LENS_ORTHOGRAPHIC: q = f; return 0;
+        case PB_LENS_STEREOGRAPHIC:  // 2 tan(t/2) / sin t = 2 / (1 + cos t)
+            if (!(1.0 + ny > 1e-8)) return 2;
+            q = 2.0 * f / (1.0 + ny);
+            return 0;
+        case PB_LENS_RECTILINEAR:  // tan t / sin t = 1 / cos t, defined for t <= 89 deg (lens.py:97-98)
+            if (ny > fg.ny_rect_in) {
+                q = f / ny;
+                return 0;
+            }
+            return (ny < fg.ny_rect_out) ? 1 : 2;
+        default: q = 1.47 * sin(0.713 * theta) * f * inv_h; return 0;
+    }
+}
+
+__device__ __forceinline__ bool lens_needs_angle(int lens) {
+    return lens == PB_LENS_EQUIDISTANT || lens == PB_LENS_THOBY;
+}
+
+// One camera sample from (cos lon, sin lon) * dist = (nx, nz) * q: 0 ok, 2 undecided; xy = packed pixel or none.
+__device__ __forceinline__ int fast_camera_xy(double nx, double nz, double q, int h, int w, double cy, double cx,
+                                              int col0, bool flip, double eps, int& xy) {
+    const double fx = fma(nx, q, cx);
+    const double fy = fma(-nz, q, cy);
+    const int ix = fast_index(fx, w, eps), iy = fast_index(fy, h, eps);
+    if (ix == -2 || iy == -2) return 2;
+    xy = pack_xy(ix, iy, col0, w, flip);
+    return 0;
+}
+
+// Source lookup of a rotated unit vector; false = undecided.
+template <int SRC_KIND>
+__device__ __forceinline__ bool fast_src_lookup(const SrcGeom& s, const FastGeom& fg, double nx, double ny, double nz,
+                                                Lookup& L) {
+    L.xy0 = L.xy1 = kNoPixel;
+    L.w0 = L.w1 = 1.0;
+    const double h2 = fma(nx, nx, nz * nz);
+    if (!(h2 > 1e-8)) return false;  // within 1e-4 rad of a pole: acos / atan2 are ill-conditioned there
+    if (SRC_KIND == PB_KIND_EQUIRECT) {
+        const double lat = acos(ny);
+        const double lon = atan2(nz, nx);
+        const int row = fast_index(lat * fg.inv_seg_h, s.H, fg.eps);
+        const int col = fast_index(fma(lon, fg.inv_seg_w, s.half_w), s.W, fg.eps);
+        if (row < 0 || col < 0) return false;  // (a coordinate outside [0, n) wraps: exact chain)
+        L.xy0 = (row << 16) | col;
+        return true;
+    }
+    const double inv_h = rsqrt(h2);
+    if (SRC_KIND == PB_KIND_CAMERA) {
+        const double theta = lens_needs_angle(s.lens) ? acos(ny) : 0.0;
+        double q;
+        const int st = fast_lens_q(s.lens, fg, ny, inv_h, theta, q);
+        if (st == 2) return false;
+        if (st == 1) return true;
+        return fast_camera_xy(nx, nz, q, s.H, s.W, s.cy, s.cx, 0, false, fg.eps, L.xy0) == 0;
+    }
+    // double source (projection.py:408-462): unit weights only, the blend band takes the exact chain
+    if (!((ny > fg.ny_band_hi) || (ny < fg.ny_band_lo))) return false;
+    const bool ang = lens_needs_angle(s.lens);
+    const double theta = ang ? acos(ny) : 0.0;
+    double ql, qr;
+    const int sl = fast_lens_q(s.lens, fg, ny, inv_h, theta, ql);
+    const int sr = fast_lens_q(s.lens, fg, -ny, inv_h, ang ? kPi - theta : 0.0, qr);
+    if (sl == 2 || sr == 2) return false;
+    if (sl == 0 && fast_camera_xy(nx, nz, ql, s.H, s.wl, s.cy, s.cxl, 0, false, fg.eps, L.xy0)) return false;
+    if (sr == 0 && fast_camera_xy(nx, nz, qr, s.H, s.wr, s.cy, s.cxr, s.wl, true, fg.eps, L.xy1)) return false;
+    return true;
+}
+
+// The whole short cut for output pixel (i, j); false = undecided (run the exact chain).
+template <int OUT_KIND, int SRC_KIND>
+__device__ __forceinline__ bool fast_lookup(const OutGeom& out, const FastGeom& fg, const Rotations& rot,
+                                            const SrcGeom& src, int i, int j, Lookup& L) {
+    double vx, vy, vz;
+    const int st = fast_out_vector<OUT_KIND>(out, fg, i, j, vx, vy, vz);
+    if (st == 2) return false;
+    if (st == 1) {
+        L.xy0 = L.xy1 = kNoPixel;
+        L.w0 = L.w1 = 1.0;
+        return true;
+    }
+    for (int n = 0; n < rot.n; ++n) {
+        const double* __restrict__ m = rot.m[n];
+        const double tx = fma(m[2], vz, fma(m[1], vy, m[0] * vx));
+        const double ty = fma(m[5], vz, fma(m[4], vy, m[3] * vx));
+        const double tz = fma(m[8], vz, fma(m[7], vy, m[6] * vx));
+        vx = tx;
+        vy = ty;
+        vz = tz;
+    }
+    return fast_src_lookup<SRC_KIND>(src, fg, vx, vy, vz, L);
+}
+
+// The exact chain, out of line: the rare fall-back of the short cut.
+template <int OUT_KIND, int SRC_KIND>
+__device__ __noinline__ Lookup exact_lookup(const OutGeom& out, const Rotations& rot, const SrcGeom& src, int i, int j) {
+    Ray r = output_ray<OUT_KIND>(out, i, j);
+    for (int n = 0; n < rot.n; ++n) r = rotate_ray(r, rot.m[n]);
+    return source_lookup<SRC_KIND>(src, r);
+}
+
+template <int OUT_KIND, int SRC_KIND>
+__device__ __forceinline__ Lookup resolve_lookup(const OutGeom& out, const FastGeom& fg, const Rotations& rot,
+                                                 const SrcGeom& src, int i, int j) {
+    Lookup L;
+    if (fg.enabled && fast_lookup<OUT_KIND, SRC_KIND>(out, fg, rot, src, i, j, L)) return L;
+    return exact_lookup<OUT_KIND, SRC_KIND>(out, rot, src, i, j);
+}
+
+}  // namespace pb

@@ -123,12 +123,92 @@ static SrcGeom derive_src(const pb_image_desc& d, int channels) {
     return s;
 }
 
+// Constants of the guarded short cut (pb_fast.cuh).  Nothing here has to be bit-identical to
+// the reference: these are decision thresholds with a guard band, not values that reach a pixel.
+static FastGeom derive_fast(const pb_image_desc& od, const OutGeom& o, const pb_image_desc& sd, const SrcGeom& s,
+                            int n_rot) {
+    FastGeom g;
+    std::memset(&g, 0, sizeof(g));
+    const double inf = INFINITY;
+    const double rel = 1e-9;  // relative guard on angles and radii
+    g.n_rot = n_rot;
+    g.eps = 1e-6;
+    g.enabled = 1;
+    if (const char* e = std::getenv("PB_EXACT_CHAIN")) {  // validation: every pixel through the exact chain
+        if (std::atoi(e) != 0) g.enabled = 0;
+    }
+    g.r2_valid = g.r2_invalid = g.r2_domain = inf;
+    if (o.kind != PB_KIND_EQUIRECT) {
+        const double f = o.f, hf = o.half_fov;
+        if (!(f > 0.0) || !std::isfinite(f) || !std::isfinite(hf)) g.enabled = 0;
+        g.inv_f = 1.0 / f;
+        // radius (in focal units) at which the latitude crosses fov / 2; inf = never
+        double d_star = inf;
+        switch (o.lens) {
+            case PB_LENS_EQUIDISTANT: d_star = hf; break;
+            case PB_LENS_EQUISOLID: d_star = hf < kPi ? 2.0 * std::sin(hf / 2.0) : inf; break;
+            case PB_LENS_ORTHOGRAPHIC: d_star = hf < kPi / 2 ? std::sin(hf) : inf; break;
+            case PB_LENS_STEREOGRAPHIC: d_star = hf < kPi ? 2.0 * std::tan(hf / 2.0) : inf; break;
+            case PB_LENS_RECTILINEAR: d_star = hf < kPi / 2 ? std::tan(hf) : inf; break;
+            default: d_star = 0.713 * hf < kPi / 2 ? 1.47 * std::sin(0.713 * hf) : inf; break;
+        }
+        if (hf < 0.0) {  // every ray is outside the fov
+            g.r2_valid = -1.0;
+            g.r2_invalid = -1.0;
+        } else if (d_star < inf) {
+            const double r_star = d_star * f;
+            g.r2_valid = (r_star * (1.0 - rel)) * (r_star * (1.0 - rel));
+            g.r2_invalid = (r_star * (1.0 + rel)) * (r_star * (1.0 + rel));
+        }
+        // edge of the well-conditioned part of the lens inverse's domain
+        const double edge = 1.0 - 1e-6;
+        switch (o.lens) {
+            case PB_LENS_EQUISOLID: g.r2_domain = 4.0 * f * f * edge; break;
+            case PB_LENS_ORTHOGRAPHIC: g.r2_domain = f * f * edge; break;
+            case PB_LENS_THOBY: g.r2_domain = 1.47 * 1.47 * f * f * edge; break;
+            case PB_LENS_EQUIDISTANT:
+                // without a rotation the latitude reaches the source as it is, not through acos
+                if (n_rot == 0) g.r2_domain = (kPi * (1.0 - rel) * f) * (kPi * (1.0 - rel) * f);
+                break;
+            default: break;
+        }
+    }
+    g.src_f = s.f;
+    g.ny_rect_in = g.ny_rect_out = 0.0;
+    g.ny_band_lo = 2.0;
+    g.ny_band_hi = -2.0;
+    if (s.kind == PB_KIND_EQUIRECT) {
+        g.inv_seg_h = 1.0 / s.seg_h;
+        g.inv_seg_w = 1.0 / s.seg_w;
+    } else {
+        if (!(s.f > 0.0) || !std::isfinite(s.f)) g.enabled = 0;
+        const double c = std::cos(s.rect_limit);
+        g.ny_rect_in = c * (1.0 + rel);
+        g.ny_rect_out = c * (1.0 - rel);
+        if (s.kind == PB_KIND_DOUBLE) {
+            if (!std::isfinite(s.mrg_lo) || !std::isfinite(s.mrg_hi_safe)) g.enabled = 0;
+            if (s.mrg_lo <= s.mrg_hi_safe) {
+                // latitudes at which either lens may get a weight != 1 (projection.py:439-456):
+                // lat in [lo, hi_safe] (left) or pi - lat in [lo, hi_safe] (right)
+                const double t_lo = std::fmin(s.mrg_lo, kPi - s.mrg_hi_safe) - rel;
+                const double t_hi = std::fmax(s.mrg_hi_safe, kPi - s.mrg_lo) + rel;
+                g.ny_band_hi = std::cos(std::fmax(t_lo, 0.0)) + rel;
+                g.ny_band_lo = std::cos(std::fmin(t_hi, kPi)) - rel;
+            }
+        }
+    }
+    (void)od;
+    (void)sd;
+    return g;
+}
+
 // ------------------------------------------------------------------------------------ kernels
 
 struct RemapArgs {
     OutGeom out;
     SrcGeom src;
     Rotations rot;
+    FastGeom fast;
     const unsigned char* src_px;
     unsigned char* dst_px;
     long long src_frame_stride, dst_frame_stride;
@@ -155,9 +235,7 @@ __global__ void __launch_bounds__(256) remap_generic_kernel(const __grid_constan
     const int i = blockIdx.y * blockDim.y + threadIdx.y;
     if (i >= a.out.H || j >= a.out.W) return;
 
-    Ray r = output_ray<OUT_KIND>(a.out, i, j);
-    for (int k = 0; k < a.rot.n; ++k) r = rotate_ray(r, a.rot.m[k]);
-    const Lookup L = source_lookup<SRC_KIND>(a.src, r);
+    const Lookup L = resolve_lookup<OUT_KIND, SRC_KIND>(a.out, a.fast, a.rot, a.src, i, j);
     const int off0 = xy_to_offset(L.xy0, a.src.W);
     const int off1 = xy_to_offset(L.xy1, a.src.W);
 
@@ -169,10 +247,6 @@ __global__ void __launch_bounds__(256) remap_generic_kernel(const __grid_constan
             if (off0 >= 0) copy_px<C>(dp, sp + (long long)off0 * C);
             else zero_px<C>(dp);
         } else {
-            if (r.invalid) {
-                zero_px<C>(dp);
-                continue;
-            }
             const unsigned char* p0 = sp + (long long)(off0 >= 0 ? off0 : 0) * C;
             const unsigned char* p1 = sp + (long long)(off1 >= 0 ? off1 : 0) * C;
 #pragma unroll
@@ -391,6 +465,7 @@ struct pb_plan {
     pb::OutGeom out;
     pb::SrcGeom src;
     pb::Rotations rot;
+    pb::FastGeom fast;   // thresholds of the guarded short cut (pb_fast.cuh)
     bool separable;      // un-rotated equirect output, camera / double source
     int stage_bytes;     // capacity of one stage buffer (a tile stages rows x its own row pitch)
     int max_units;       // widest staged row of any tile, in 16-byte units (one tensor map per width)
@@ -421,6 +496,7 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     p.src = derive_src(d.src, d.channels);
     p.rot.n = d.n_rotations;
     std::memcpy(p.rot.m, d.rotations, sizeof(p.rot.m));
+    p.fast = derive_fast(d.out, p.out, d.src, p.src, d.n_rotations);
     p.separable = d.out.kind == PB_KIND_EQUIRECT && d.n_rotations == 0 && d.src.kind != PB_KIND_EQUIRECT &&
                   d.channels == 3;
     p.stage_bytes = 24 * 1024;  // un-tuned default (pb_remap_u8 without a plan)
@@ -513,6 +589,7 @@ static void tune_stage(pb_plan& p, cudaStream_t st) {
     a.out = p.out;
     a.src = p.src;
     a.rot = p.rot;
+    a.fast = p.fast;
     a.col_tab = p.tables;
     a.row_tab = p.tables ? p.tables + 2 * (size_t)p.out.W : nullptr;
     a.n_frames = 0;
@@ -567,6 +644,7 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         a.out = p.out;
         a.src = p.src;
         a.rot = p.rot;
+        a.fast = p.fast;
         a.col_tab = tables;
         a.row_tab = tables ? tables + 2 * (size_t)p.out.W : nullptr;
         a.tile_fp = tables ? footprint_table(p, tables) : nullptr;
@@ -619,6 +697,7 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
     a.out = p.out;
     a.src = p.src;
     a.rot = p.rot;
+    a.fast = p.fast;
     a.src_px = src;
     a.dst_px = dst;
     a.src_frame_stride = src_frame_stride;

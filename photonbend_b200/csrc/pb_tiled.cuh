@@ -36,6 +36,7 @@
 #include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through the runtime)
 
 #include "pb_device.cuh"
+#include "pb_fast.cuh"
 #include "pb_ptx.cuh"
 
 namespace pb {
@@ -64,6 +65,7 @@ struct TiledArgs {
     OutGeom out;
     SrcGeom src;
     Rotations rot;
+    FastGeom fast;    // guarded short cut of the per-pixel chain (pb_fast.cuh)
     const double* col_tab;  // separable: [W][2]  (cos lon_j, sin lon_j)
     const double* row_tab;  // separable: [H][4]  camera: (dist, -, -, -); double: (dist_l, dist_r, w_l, w_r)
     const unsigned char* src_px;
@@ -471,9 +473,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         for (int p = 0; p < kPxPerThread; ++p) {
             const int i = min(y0 + rg + (p >> 2) * kRowGroups, a.out.H - 1);
             const int j = min(jx + (p & 3), a.out.W - 1);
-            Ray r = output_ray<OUT_KIND>(a.out, i, j);
-            for (int n = 0; n < a.rot.n; ++n) r = rotate_ray(r, a.rot.m[n]);
-            const Lookup L = source_lookup<SRC_KIND>(a.src, r);
+            const Lookup L = resolve_lookup<OUT_KIND, SRC_KIND>(a.out, a.fast, a.rot, a.src, i, j);
             xy_scratch[p * kTileThreads + tid] = L.xy0;
             if (L.xy0 >= 0) fp[0].add(L.xy0 & 0xffff, L.xy0 >> 16);
             if (DBL) {

@@ -289,3 +289,64 @@ def test_tiled_fast_path_mid_size_batches(torch_cuda, src_kind):
     # a rotated double-fisheye source may differ by the 1-LSB blend-truncation class only
     assert n_bad == 0 or (src_kind == "double" and max_abs == 1 and n_bad / (got.shape[0] * got.shape[1]) <= 1e-4), \
         (src_kind, n_bad, max_abs)
+
+
+def _mid_size_geometries():
+    """Every lens on both sides at a size that takes the tiled (TMA-staged) path."""
+    rad = case_matrix.rad
+    outs, srcs = [], []
+    for lens, fov in (("equidistant", 360), ("equidistant", 150), ("equisolid", 180), ("equisolid", 360),
+                      ("orthographic", 180), ("orthographic", 120), ("stereographic", 200),
+                      ("rectilinear", 140), ("thoby", 180)):
+        outs.append({"kind": "camera", "height": 200, "width": 272, "lens": lens, "fov": rad(fov),
+                     "magnitude": 135.5})
+        srcs.append({"kind": "camera", "height": 240, "width": 256, "lens": lens, "fov": rad(fov),
+                     "magnitude": 127.5})
+    for lens in ("equidistant", "equisolid", "stereographic"):
+        outs.append({"kind": "double", "height": 160, "width": 320, "lens": lens, "fov": rad(195)})
+        srcs.append({"kind": "double", "height": 192, "width": 384, "lens": lens, "fov": rad(190)})
+    outs.append({"kind": "equirect", "height": 160, "width": 320})
+    srcs.append({"kind": "equirect", "height": 192, "width": 384})
+    return outs, srcs
+
+
+def test_fast_path_equals_exact_chain(torch_cuda, monkeypatch):
+    """csrc/pb_fast.cuh: the guarded short cut (unit-vector form, no polar round trips) must give
+    the pixels of the exact chain bit for bit -- every undecided pixel falls back to it.  Checked
+    on every lens pair x {no, one, two} rotations at tiled-path sizes, on the whole small matrix
+    (generic kernel: rows not 16-byte aligned), and on the two rotated BASELINE configurations."""
+    from photonbend_b200 import engine, workloads
+
+    def both(og, rots, sg, image):
+        monkeypatch.delenv("PB_EXACT_CHAIN", raising=False)
+        engine.clear_plan_cache()
+        fast = helpers.product_remap(og, rots, sg, image)
+        monkeypatch.setenv("PB_EXACT_CHAIN", "1")
+        engine.clear_plan_cache()
+        exact = helpers.product_remap(og, rots, sg, image)
+        monkeypatch.delenv("PB_EXACT_CHAIN", raising=False)
+        engine.clear_plan_cache()
+        return fast, exact
+
+    outs, srcs = _mid_size_geometries()
+    rotsets = ((), ((0.3, -0.2, 1.0),), ((case_matrix.rad(-90), 0.0, case_matrix.rad(195)), (0.1, 0.2, 0.3)))
+    n = 0
+    for a, og in enumerate(outs):
+        for b, sg in enumerate(srcs):
+            image = case_matrix.case_image(sg, 1000 + b)
+            for rots in rotsets:
+                fast, exact = both(og, rots, sg, image)
+                assert np.array_equal(fast, exact), (og, rots, sg, int((fast != exact).any(axis=2).sum()))
+                n += 1
+    for cid, og, rots, sg, seed in CASES[::3]:
+        image = case_matrix.case_image(sg, seed)
+        fast, exact = both(og, rots, sg, image)
+        assert np.array_equal(fast, exact), cid
+        n += 1
+    for name in ("cfg2", "cfg3"):
+        wl = workloads.WORKLOADS[name]
+        image = workloads.source_image(wl)
+        fast, exact = both(wl["out"], wl["rotations"], wl["src"], image)
+        assert np.array_equal(fast, exact), name
+        n += 1
+    print(f"short cut == exact chain on {n} cases")
