@@ -17,7 +17,7 @@
 // relative), so its truncated source index can differ where a coordinate sits within ~1e-9 px of
 // an integer.  Therefore every decision the short cut takes -- each truncation, the fov test, the
 // lens domains, the blend band of a double source -- is only accepted when the value is further
-// than a guard band from the decision boundary (eps = 1e-6 px, 1e-9 relative for angles; the two
+// than a guard band from the decision boundary (2^-19 px, 1e-9 relative for angles; the two
 // chains differ by < 1e-8 px wherever the conditioning guards below let the short cut run).
 // Otherwise the pixel is "undecided" and the caller runs the exact chain for it (~4e-6 of the
 // pixels).  Results are therefore those of the exact chain, bit for bit
@@ -31,7 +31,8 @@ namespace pb {
 struct FastGeom {
     int enabled;
     int n_rot;
-    double eps;                    // guard band around integer source coordinates, pixels
+    int has_rot;
+    double rot[9];                 // all rotations composed, row-major: R_n ... R_1
     // output side (camera / double)
     double inv_f;                  // 1 / out.f
     double r2_valid, r2_invalid;   // r^2 < r2_valid: inside the fov; r^2 > r2_invalid: outside; else undecided
@@ -47,14 +48,19 @@ constexpr double kTwo52 = 4503599627370496.0;
 
 // Index of source coordinate v along an axis of n pixels, under the reference's rule (truncate
 // toward zero, then 0 <= index < n; projection.py:223-231, 254-259):
-// >= 0 the index, -1 outside the image, -2 undecided (within eps of an integer, or not finite).
-__device__ __forceinline__ int fast_index(double v, int n, double eps) {
-    const double av = fabs(v);
-    const double nearest = __dadd_rn(__dadd_rn(av, kTwo52), -kTwo52);
-    const double dist = fabs(__dadd_rn(av, -nearest));
-    if (!(dist > eps) || !(av < 2147483648.0)) return -2;
-    const int idx = __double2loint(__dadd_rz(av, kTwo52));
-    return (v > -1.0 && v < (double)n) ? idx : -1;
+// >= 0 the index, -1 outside the image, -2 undecided (within 2^-19 px of an integer, or not finite).
+// One FP64 add: |v| + 1.5 * 2^32 lies in [1.5 * 2^32, 2^33) for |v| < 2^31, where one ulp is 2^-20,
+// so the mantissa of the sum is |v| + 2^31 in fixed point with 20 fraction bits.
+__device__ __forceinline__ int fast_index(double v, int n) {
+    const double g = __dadd_rn(fabs(v), 6442450944.0);
+    const unsigned lo = (unsigned)__double2loint(g), hi = (unsigned)__double2hiint(g);
+    const unsigned frac = lo & 0xFFFFFu;  // rounded to nearest: the true fraction is within half a unit
+    const int idx = (int)(__funnelshift_r(lo, hi, 20) ^ 0x80000000u);
+    const bool finite = (hi - 0x41F80000u) < 0x00080000u;      // |v| < 2^31, not NaN
+    const bool off_boundary = (frac - 2u) < (0x100000u - 3u);  // 2 <= frac <= 2^20 - 2
+    if (!(finite && off_boundary)) return -2;
+    const bool in = (__double2hiint(v) < 0) ? (idx == 0) : (idx < n);  // (-1, 0) truncates to 0
+    return in ? idx : -1;
 }
 
 // Unit vector of the ray of output pixel (i, j) before any rotation:
@@ -76,9 +82,11 @@ __device__ __forceinline__ int fast_out_vector(const OutGeom& g, const FastGeom&
     }
     const bool right = (OUT_KIND == PB_KIND_DOUBLE) && j >= g.half_w;
     const int n_cols = (OUT_KIND == PB_KIND_DOUBLE) ? g.half_w : g.W;
-    double x = linspace_at(g.x_start, g.x_stop, g.x_step, n_cols, right ? j - g.half_w : j);
+    // pixel-centre coordinates: the linspace steps of projection.py:177-183 are exactly +-1
+    (void)n_cols;
+    double x = (double)(right ? j - g.half_w : j) + g.x_start;
     if (right) x = -x;
-    const double y = linspace_at(g.y_start, g.y_stop, g.y_step, g.H, i);
+    const double y = g.y_start - (double)i;
     const double r2 = fma(x, x, y * y);
     if (!(r2 < fg.r2_domain)) return 2;
     if (!(r2 < fg.r2_valid)) return (r2 > fg.r2_invalid) ? 1 : 2;
@@ -158,10 +166,10 @@ __device__ __forceinline__ bool lens_needs_angle(int lens) {
 
 // One camera sample from (cos lon, sin lon) * dist = (nx, nz) * q: 0 ok, 2 undecided; xy = packed pixel or none.
 __device__ __forceinline__ int fast_camera_xy(double nx, double nz, double q, int h, int w, double cy, double cx,
-                                              int col0, bool flip, double eps, int& xy) {
+                                              int col0, bool flip, int& xy) {
     const double fx = fma(nx, q, cx);
     const double fy = fma(-nz, q, cy);
-    const int ix = fast_index(fx, w, eps), iy = fast_index(fy, h, eps);
+    const int ix = fast_index(fx, w), iy = fast_index(fy, h);
     if (ix == -2 || iy == -2) return 2;
     xy = pack_xy(ix, iy, col0, w, flip);
     return 0;
@@ -178,8 +186,8 @@ __device__ __forceinline__ bool fast_src_lookup(const SrcGeom& s, const FastGeom
     if (SRC_KIND == PB_KIND_EQUIRECT) {
         const double lat = acos(ny);
         const double lon = atan2(nz, nx);
-        const int row = fast_index(lat * fg.inv_seg_h, s.H, fg.eps);
-        const int col = fast_index(fma(lon, fg.inv_seg_w, s.half_w), s.W, fg.eps);
+        const int row = fast_index(lat * fg.inv_seg_h, s.H);
+        const int col = fast_index(fma(lon, fg.inv_seg_w, s.half_w), s.W);
         if (row < 0 || col < 0) return false;  // (a coordinate outside [0, n) wraps: exact chain)
         L.xy0 = (row << 16) | col;
         return true;
@@ -191,7 +199,7 @@ __device__ __forceinline__ bool fast_src_lookup(const SrcGeom& s, const FastGeom
         const int st = fast_lens_q(s.lens, fg, ny, inv_h, theta, q);
         if (st == 2) return false;
         if (st == 1) return true;
-        return fast_camera_xy(nx, nz, q, s.H, s.W, s.cy, s.cx, 0, false, fg.eps, L.xy0) == 0;
+        return fast_camera_xy(nx, nz, q, s.H, s.W, s.cy, s.cx, 0, false, L.xy0) == 0;
     }
     // double source (projection.py:408-462): unit weights only, the blend band takes the exact chain
     if (!((ny > fg.ny_band_hi) || (ny < fg.ny_band_lo))) return false;
@@ -201,8 +209,8 @@ __device__ __forceinline__ bool fast_src_lookup(const SrcGeom& s, const FastGeom
     const int sl = fast_lens_q(s.lens, fg, ny, inv_h, theta, ql);
     const int sr = fast_lens_q(s.lens, fg, -ny, inv_h, ang ? kPi - theta : 0.0, qr);
     if (sl == 2 || sr == 2) return false;
-    if (sl == 0 && fast_camera_xy(nx, nz, ql, s.H, s.wl, s.cy, s.cxl, 0, false, fg.eps, L.xy0)) return false;
-    if (sr == 0 && fast_camera_xy(nx, nz, qr, s.H, s.wr, s.cy, s.cxr, s.wl, true, fg.eps, L.xy1)) return false;
+    if (sl == 0 && fast_camera_xy(nx, nz, ql, s.H, s.wl, s.cy, s.cxl, 0, false, L.xy0)) return false;
+    if (sr == 0 && fast_camera_xy(nx, nz, qr, s.H, s.wr, s.cy, s.cxr, s.wl, true, L.xy1)) return false;
     return true;
 }
 
@@ -218,8 +226,8 @@ __device__ __forceinline__ bool fast_lookup(const OutGeom& out, const FastGeom& 
         L.w0 = L.w1 = 1.0;
         return true;
     }
-    for (int n = 0; n < rot.n; ++n) {
-        const double* __restrict__ m = rot.m[n];
+    if (fg.has_rot) {
+        const double* __restrict__ m = fg.rot;
         const double tx = fma(m[2], vz, fma(m[1], vy, m[0] * vx));
         const double ty = fma(m[5], vz, fma(m[4], vy, m[3] * vx));
         const double tz = fma(m[8], vz, fma(m[7], vy, m[6] * vx));
@@ -227,6 +235,7 @@ __device__ __forceinline__ bool fast_lookup(const OutGeom& out, const FastGeom& 
         vy = ty;
         vz = tz;
     }
+    (void)rot;
     return fast_src_lookup<SRC_KIND>(src, fg, vx, vy, vz, L);
 }
 

@@ -126,14 +126,27 @@ static SrcGeom derive_src(const pb_image_desc& d, int channels) {
 // Constants of the guarded short cut (pb_fast.cuh).  Nothing here has to be bit-identical to
 // the reference: these are decision thresholds with a guard band, not values that reach a pixel.
 static FastGeom derive_fast(const pb_image_desc& od, const OutGeom& o, const pb_image_desc& sd, const SrcGeom& s,
-                            int n_rot) {
+                            int n_rot, const double (*rotations)[9]) {
     FastGeom g;
     std::memset(&g, 0, sizeof(g));
     const double inf = INFINITY;
     const double rel = 1e-9;  // relative guard on angles and radii
     g.n_rot = n_rot;
-    g.eps = 1e-6;
     g.enabled = 1;
+    // R_total = R_n ... R_1: the short cut applies all rotations as one matrix
+    double acc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int k = 0; k < n_rot; ++k) {
+        double nxt[9];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                nxt[3 * r + c] = rotations[k][3 * r] * acc[c] + rotations[k][3 * r + 1] * acc[3 + c] +
+                                 rotations[k][3 * r + 2] * acc[6 + c];
+        std::memcpy(acc, nxt, sizeof(acc));
+    }
+    g.has_rot = n_rot > 0;
+    std::memcpy(g.rot, acc, sizeof(acc));
+    for (int e = 0; e < 9; ++e)
+        if (!std::isfinite(acc[e])) g.enabled = 0;
     if (const char* e = std::getenv("PB_EXACT_CHAIN")) {  // validation: every pixel through the exact chain
         if (std::atoi(e) != 0) g.enabled = 0;
     }
@@ -496,7 +509,7 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     p.src = derive_src(d.src, d.channels);
     p.rot.n = d.n_rotations;
     std::memcpy(p.rot.m, d.rotations, sizeof(p.rot.m));
-    p.fast = derive_fast(d.out, p.out, d.src, p.src, d.n_rotations);
+    p.fast = derive_fast(d.out, p.out, d.src, p.src, d.n_rotations, d.rotations);
     p.separable = d.out.kind == PB_KIND_EQUIRECT && d.n_rotations == 0 && d.src.kind != PB_KIND_EQUIRECT &&
                   d.channels == 3;
     p.stage_bytes = 24 * 1024;  // un-tuned default (pb_remap_u8 without a plan)
