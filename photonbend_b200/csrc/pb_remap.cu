@@ -12,6 +12,7 @@
 
 #include "pb_device.cuh"
 #include "pb_tiled.cuh"
+#include "pb_sep1.cuh"
 
 namespace pb {
 
@@ -469,6 +470,32 @@ static cudaError_t launch_tiled(const TiledArgs& a, bool separable, cudaStream_t
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// persistent single-frame kernel: as many CTAs as the device holds at once
+template <int SRC_KIND>
+static cudaError_t launch_sep1_one(const TiledArgs& a, cudaStream_t st) {
+    const int smem = sep1_smem_bytes(a.sep1_cap);
+    static int max_smem_set = 0;
+    if (smem > max_smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(remap_sep1_kernel<SRC_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        max_smem_set = smem;
+    }
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, remap_sep1_kernel<SRC_KIND>, kTileThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    int grid = sms * per_sm;
+    if (const char* env = std::getenv("PB_SEP1_GRID")) grid = std::atoi(env);  // tuning experiments
+    const int n_tiles = a.tiles_x * a.tiles_y;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid < 1) grid = 1;
+    remap_sep1_kernel<SRC_KIND><<<grid, kTileThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 }  // namespace pb
 
 // A plan: one validated geometry with everything derived from it (host constants, and for an
@@ -483,6 +510,7 @@ struct pb_plan {
     int stage_bytes;     // capacity of one stage buffer (a tile stages rows x its own row pitch)
     int max_units;       // widest staged row of any tile, in 16-byte units (one tensor map per width)
     int raster_band;     // tile rows per raster band (see remap_tiled_kernel)
+    int sep1_cap;        // single-frame separable kernel: bytes per stage buffer
     double* tables;      // device: col_tab [W][2], row_tab [H][4], then the per-tile footprints; null unless separable
     int device;
 };
@@ -515,6 +543,7 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     p.stage_bytes = 24 * 1024;  // un-tuned default (pb_remap_u8 without a plan)
     p.max_units = 19;           // rows of up to 304 bytes = 101 source pixels
     p.raster_band = 16;
+    p.sep1_cap = (d.src.kind == PB_KIND_DOUBLE ? 48 : 24) * 1024;  // un-tuned default
     if (const char* e = std::getenv("PB_RASTER_BAND")) p.raster_band = std::atoi(e);  // tuning experiments
     p.tables = nullptr;
     p.device = -1;
@@ -528,9 +557,13 @@ static int tiles_y(const pb_plan& p) { return (p.out.H + kTileH - 1) / kTileH; }
 static int footprint_entries(const pb_plan& p) {
     return tiles_x(p) * tiles_y(p) * (p.src.kind == PB_KIND_DOUBLE ? 2 : 1);
 }
-// col_tab [W][2] + row_tab [H][4] doubles, then one int4 footprint per (tile, slot)
+// col_tab [W][2] + row_tab [H][4] doubles, then one int4 footprint per (tile, slot), then the same
+// per (tile in launch order, slot) for the single-frame kernel
 static size_t table_doubles(const pb_plan& p) {
-    return 2 * (size_t)p.out.W + 4 * (size_t)p.out.H + 2 * (size_t)footprint_entries(p);
+    return 2 * (size_t)p.out.W + 4 * (size_t)p.out.H + 4 * (size_t)footprint_entries(p);
+}
+static const int4* sep1_table(const pb_plan& p, const double* tables) {
+    return reinterpret_cast<const int4*>(tables + 2 * (size_t)p.out.W + 4 * (size_t)p.out.H) + footprint_entries(p);
 }
 static const int4* footprint_table(const pb_plan& p, const double* tables) {
     return reinterpret_cast<const int4*>(tables + 2 * (size_t)p.out.W + 4 * (size_t)p.out.H);
@@ -585,6 +618,36 @@ static void tune_stage(pb_plan& p, cudaStream_t st) {
                 if (fits && units > h[kProbeSizeBins]) h[kProbeSizeBins] = units;
             }
             pick_stage(p, h);
+            // single-frame kernel: one buffer holds every rectangle of a tile; size it for 99.5 % of the tiles
+            const int nslot = p.src.kind == PB_KIND_DOUBLE ? 2 : 1;
+            const int n_tiles = n_entries / nslot;
+            int* hist = new (std::nothrow) int[129]();
+            if (hist) {
+                int counted = 0;
+                for (int t = 0; t < n_tiles; ++t) {
+                    long long total = 0;
+                    for (int s = 0; s < nslot; ++s) {
+                        const int4& fp = host[t * nslot + s];
+                        if (fp.z == 0) continue;
+                        const int units = stage_units(fp.w >> 1);
+                        total += units <= kMaxStageUnits ? (long long)fp.z * kBoxRows * 16 * units : (1LL << 40);
+                    }
+                    if (total == 0) continue;
+                    const long long kib = (total + 1023) >> 10;
+                    hist[kib > 128 ? 128 : (int)kib] += 1;
+                    counted += 1;
+                }
+                int acc = 0, kib = 128;
+                for (int k = 0; k <= 128; ++k) {
+                    acc += hist[k];
+                    if (acc >= counted - counted / 200) { kib = k; break; }
+                }
+                if (kib < 4) kib = 4;
+                if (kib > 96) kib = 96;
+                if (const char* e = std::getenv("PB_SEP1_KIB")) kib = std::atoi(e);  // tuning experiments
+                p.sep1_cap = kib * 1024;
+                delete[] hist;
+            }
         } else {
             (void)cudaGetLastError();
         }
@@ -639,6 +702,13 @@ static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st
     const int n_entries = footprint_entries(p);
     pb_footprint_kernel<<<(n_entries + 7) / 8, 256, 0, st>>>(a, const_cast<int4*>(footprint_table(p, tables)),
                                                            tiles_x(p), n_entries);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int n_tiles = tiles_x(p) * tiles_y(p);
+    pb_sep1_table_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(footprint_table(p, tables),
+                                                              const_cast<int4*>(sep1_table(p, tables)), tiles_x(p),
+                                                              tiles_y(p), p.raster_band,
+                                                              p.src.kind == PB_KIND_DOUBLE ? 2 : 1);
     return cudaGetLastError();
 }
 
@@ -661,6 +731,8 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         a.col_tab = tables;
         a.row_tab = tables ? tables + 2 * (size_t)p.out.W : nullptr;
         a.tile_fp = tables ? footprint_table(p, tables) : nullptr;
+        a.sep1_tab = tables ? sep1_table(p, tables) : nullptr;
+        a.sep1_cap = p.sep1_cap;
         a.src_px = src;
         a.src_frame_stride = src_frame_stride;
         a.n_frames = n_frames;
@@ -700,7 +772,14 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         if (maps_ok &&
             encode_frames_map(&a.dst_map, dst, dst_pitch, p.out.H, n_frames, dst_frame_stride, 1, kOutRowBytes,
                               kTileH)) {
-            cudaError_t e = launch_tiled(a, p.separable && tables != nullptr, st);
+            const bool sep = p.separable && tables != nullptr;
+            static const bool sep1_off = std::getenv("PB_SEP1") && std::atoi(std::getenv("PB_SEP1")) == 0;
+            cudaError_t e;
+            if (sep && n_frames == 1 && !sep1_off && p.out.W / kTileW < 65536 && p.out.H / kTileH < 32768)
+                e = a.src.kind == PB_KIND_CAMERA ? launch_sep1_one<PB_KIND_CAMERA>(a, st)
+                                                 : launch_sep1_one<PB_KIND_DOUBLE>(a, st);
+            else
+                e = launch_tiled(a, sep, st);
             if (e != cudaSuccess) return cuda_fail(e, "tiled remap launch");
             return PB_OK;
         }

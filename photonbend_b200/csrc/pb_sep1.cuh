@@ -1,0 +1,272 @@
+// pb_sep1.cuh -- ONE frame through a separable geometry (un-rotated equirect output from a camera
+// or double-fisheye source): what a make-pano call does (BASELINE configs 1 and 4, the 8K target).
+//
+// The batched kernel (pb_tiled.cuh) resolves a tile's source offsets once and applies them to
+// every frame; with a single frame that set-up is all there is, and ncu shows the launch bound by
+// instruction issue (59 thread-instructions per pixel around 6 FP64 operations) and by the
+// load -> gather -> store latency chain of one-tile CTAs (profiles/r1_ncu_full_T_1frame.txt).
+// This kernel does the same work with
+//   * persistent CTAs that walk tiles u = blockIdx.x, + gridDim.x, ... of a per-plan table in
+//     launch order (tile position and footprint pre-decoded: no raster divisions, no footprint
+//     arithmetic in the kernel),
+//   * a two-deep pipeline per CTA: the TMA box loads of tile n+1 are in flight, and those of tile
+//     n+2 are issued, while tile n is gathered; its TMA tile store drains under tile n+1,
+//   * per pixel: 4 FP64 multiply/adds + 2 FP64 truncating adds, two integer multiply-adds, two
+//     LDS.32 and a funnel shift -- offsets are consumed as they are produced (no offset arrays),
+//   * one block barrier per tile.
+// Arithmetic per pixel is exactly that of pb_tiled.cuh's separable mode (same tables, same
+// operations in the same order), so results are bit-identical by construction.
+#pragma once
+
+#include "pb_tiled.cuh"
+
+namespace pb {
+
+// Per (tile in launch order, slot) descriptor, written once per plan by pb_sep1_table_kernel:
+//   x: first source row (bits 0-14) | number of 16-row boxes << 16 | staged-row units << 24 | all_valid << 30
+//   y: first staged byte of a source row (multiple of 16)
+//   z: tile_x | tile_y << 16
+//   w: by0 * pitch + xb0  (byte offset of the rectangle's origin in "staged pitch" coordinates)
+__global__ void __launch_bounds__(256) pb_sep1_table_kernel(const int4* __restrict__ tile_fp, int4* __restrict__ tab,
+                                                            int tiles_x, int tiles_y, int raster_band, int nslot) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= tiles_x * tiles_y) return;
+    int tile_x, tile_y;
+    if (raster_band > 0) {
+        const int per_band = raster_band * tiles_x;
+        const int band = u / per_band, within = u - band * per_band;
+        const int bh = min(raster_band, tiles_y - band * raster_band);
+        tile_x = within / bh;
+        tile_y = band * raster_band + (within - tile_x * bh);
+    } else {
+        tile_y = u / tiles_x;
+        tile_x = u - tile_y * tiles_x;
+    }
+    for (int s = 0; s < nslot; ++s) {
+        const int4 fp = tile_fp[(tile_y * tiles_x + tile_x) * nslot + s];
+        int4 d = make_int4(0, 0, tile_x | (tile_y << 16), 0);
+        if (fp.z > 0) {
+            const int units = stage_units(fp.w >> 1);
+            const bool fits = units <= kMaxStageUnits && fp.z <= 255;
+            // a footprint that cannot be staged keeps nbox = 255 / units = 63: the kernel then gathers from global memory
+            d.x = fp.x | ((fits ? fp.z : 255) << 16) | ((fits ? units : 63) << 24) | ((fp.w & 1) << 30);
+            d.y = fp.y;
+            d.w = fp.x * 16 * units + fp.y;
+        }
+        tab[u * nslot + s] = d;
+    }
+}
+
+struct Sep1Slot {
+    int nbox, pitch, rect, by0, xb0, origin;
+    bool all_valid;
+    __device__ __forceinline__ void decode(const int4 d) {
+        nbox = (d.x >> 16) & 0xff;
+        pitch = ((d.x >> 24) & 0x3f) << 4;
+        rect = nbox * kBoxRows * pitch;
+        by0 = d.x & 0x7fff;
+        xb0 = d.y;
+        origin = d.w;
+        all_valid = (d.x >> 30) & 1;
+    }
+};
+
+template <int SRC_KIND>
+__global__ void __launch_bounds__(kTileThreads, (SRC_KIND == PB_KIND_DOUBLE) ? 3 : 5)
+remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
+    constexpr bool DBL = (SRC_KIND == PB_KIND_DOUBLE);
+    constexpr int NSLOT = DBL ? 2 : 1;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    // [ out tile 0 ][ out tile 1 ][ stage 0: 128 zero bytes + cap ][ stage 1 ][ ring of 4 tile descriptors ][ 2 mbarriers ]
+    const int cap = a.sep1_cap;
+    const int buf_bytes = 128 + cap;
+    unsigned char* out_tiles = smem;
+    unsigned char* stages = smem + 2 * kOutTileBytes;
+    int4* ring = reinterpret_cast<int4*>(stages + 2 * buf_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 8);
+
+    const int tid = threadIdx.x;
+    const int qc = tid & (kQuadsPerRow - 1);
+    const int rg = tid >> 3;
+    const int G = gridDim.x;
+    const int n_tiles = a.tiles_x * a.tiles_y;
+    const int4* __restrict__ tab = a.sep1_tab;
+
+    if (tid == 0) {
+        ptx::prefetch_tensormap(&a.dst_map);
+        ptx::mbarrier_init(&bars[0], 1);
+        ptx::mbarrier_init(&bars[1], 1);
+        ptx::fence_mbarrier_init();
+    }
+    if (tid < 16) reinterpret_cast<int4*>(stages + (tid >> 3) * buf_bytes)[tid & 7] = make_int4(0, 0, 0, 0);
+    if (tid < 3 * NSLOT) {  // descriptors of this CTA's first three tiles
+        const int k = tid / NSLOT, s = tid - k * NSLOT;
+        const int u = blockIdx.x + k * G;
+        ring[k * 2 + s] = (u < n_tiles) ? __ldg(tab + u * NSLOT + s) : make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    // one thread: the box loads of the tile whose descriptors sit in ring slot r, into stage buffer b
+    auto issue = [&](int r, int b) {
+        Sep1Slot s0, s1;
+        s0.decode(ring[r * 2]);
+        s1.decode(DBL ? ring[r * 2 + 1] : make_int4(0, 0, 0, 0));
+        const int total = s0.rect + s1.rect;
+        if (total == 0 || total > cap) return;  // nothing visible, or gathered from global memory
+        ptx::mbarrier_arrive_expect_tx(&bars[b], (unsigned)total);
+        const uint64_t keep = ptx::policy_evict_last();
+        unsigned char* base = stages + b * buf_bytes + 128;
+        if (s0.nbox > 0) {
+            const CUtensorMap* map = &a.src_maps[(s0.pitch >> 5) - (kMinStageUnits >> 1)];
+            for (int k = 0; k < s0.nbox; ++k)
+                ptx::tma_load_3d_hint(base + k * kBoxRows * s0.pitch, map, s0.xb0 >> 1, s0.by0 + k * kBoxRows, 0, &bars[b], keep);
+        }
+        if (DBL && s1.nbox > 0) {
+            const CUtensorMap* map = &a.src_maps[(s1.pitch >> 5) - (kMinStageUnits >> 1)];
+            for (int k = 0; k < s1.nbox; ++k)
+                ptx::tma_load_3d_hint(base + s0.rect + k * kBoxRows * s1.pitch, map, s1.xb0 >> 1, s1.by0 + k * kBoxRows, 0,
+                                      &bars[b], keep);
+        }
+    };
+    if (tid == 0) {
+        issue(0, 0);
+        if (blockIdx.x + G < n_tiles) issue(1, 1);
+    }
+
+    const uint64_t drop = ptx::policy_evict_first();
+    const unsigned stages_sa = ptx::smem_addr(stages);
+    const unsigned out_sa = ptx::smem_addr(out_tiles) + rg * kOutRowBytes + qc * 12;
+    const double cy = a.src.cy;
+    unsigned phase = 0;  // bit b: parity the next wait on stage buffer b expects
+
+    int it = 0;
+    for (int u = blockIdx.x; u < n_tiles; u += G, ++it) {
+        const int b = it & 1;
+        const int4 d0 = ring[(it & 3) * 2];
+        const int4 d1 = DBL ? ring[(it & 3) * 2 + 1] : make_int4(0, 0, 0, 0);
+        // the descriptor of the tile three ahead travels while this tile is processed
+        int4 pre = make_int4(0, 0, 0, 0);
+        if (tid < NSLOT && u + 3 * G < n_tiles) pre = __ldg(tab + (u + 3 * G) * NSLOT + tid);
+
+        Sep1Slot sl[2];
+        sl[0].decode(d0);
+        sl[1].decode(d1);
+        const int x0 = (d0.z & 0xffff) * kTileW, y0 = (d0.z >> 16) * kTileH;
+        const int total = sl[0].rect + sl[1].rect;
+        const bool staged = total <= cap;  // block-uniform
+
+        // tables: 4 columns, 2 rows per thread (rows / columns past the image edge repeat the last one: TMA clips them)
+        const int jx = x0 + 4 * qc;
+        double2 cs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cs[k] = __ldg(reinterpret_cast<const double2*>(a.col_tab) + min(jx + k, a.out.W - 1));
+        double2 r01[kRowsPerThread], r23[kRowsPerThread];
+#pragma unroll
+        for (int q = 0; q < kRowsPerThread; ++q) {
+            const int i = min(y0 + rg + q * kRowGroups, a.out.H - 1);
+            r01[q] = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i);
+            if (DBL) r23[q] = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i + 1);
+        }
+
+        if (staged && total > 0) {
+            ptx::mbarrier_wait_sa(ptx::smem_addr(&bars[b]), (phase >> b) & 1u);
+            phase ^= 1u << b;
+        }
+        const unsigned stage_sa = stages_sa + b * buf_bytes;
+        const unsigned char* __restrict__ frame = a.src_px;
+
+        // v[q][k]: the pixel (low 3 bytes) of row q, column k of this thread
+        unsigned v[kRowsPerThread][4];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            const Sep1Slot& S = sl[s];
+            const int w = DBL ? (s ? a.src.wr : a.src.wl) : a.src.W;
+            const double cx = DBL ? (s ? a.src.cxr : a.src.cxl) : a.src.cx;
+            unsigned g[kRowsPerThread][4];
+            if (S.nbox == 0) {  // block-uniform: nothing of this lens is visible from the tile
+#pragma unroll
+                for (int q = 0; q < kRowsPerThread; ++q)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) g[q][k] = 0u;
+            } else if (staged) {
+                // byte offset inside the stage buffer = py * pitch + px * 3 + (128 + rectangle start - origin)
+                const int base = 128 + (s ? sl[0].rect : 0) - S.origin;
+                if (S.all_valid) {
+#pragma unroll
+                    for (int q = 0; q < kRowsPerThread; ++q)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            double fx, fy;
+                            camera_fxy(cs[k].x, cs[k].y, s ? r01[q].y : r01[q].x, cy, cx, fx, fy);
+                            int px = trunc_abs(fx);
+                            if (s) px = a.src.W - 1 - px;
+                            const int off = trunc_abs(fy) * S.pitch + (px * 3 + base);
+                            g[q][k] = ptx::lds_pixel(stage_sa, (unsigned)off & ~3u, (unsigned)off << 3);
+                        }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < kRowsPerThread; ++q)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            double fx, fy;
+                            camera_fxy(cs[k].x, cs[k].y, s ? r01[q].y : r01[q].x, cy, cx, fx, fy);
+                            int px = trunc_abs(fx);
+                            if (s) px = a.src.W - 1 - px;
+                            int off = trunc_abs(fy) * S.pitch + (px * 3 + base);
+                            off = inside_image(fx, fy, w, a.src.H) ? off : 0;  // 0: the buffer's zero bytes
+                            g[q][k] = ptx::lds_pixel(stage_sa, (unsigned)off & ~3u, (unsigned)off << 3);
+                        }
+                }
+            } else {
+                // footprint too large to stage (a pole of the source): straight from global memory
+#pragma unroll
+                for (int q = 0; q < kRowsPerThread; ++q)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        double fx, fy;
+                        camera_fxy(cs[k].x, cs[k].y, s ? r01[q].y : r01[q].x, cy, cx, fx, fy);
+                        int px = trunc_abs(fx);
+                        if (s) px = a.src.W - 1 - px;
+                        const int py = trunc_abs(fy);
+                        g[q][k] = inside_image(fx, fy, w, a.src.H) ? pick_px_global(frame, py * a.src_pitch + px * 3) : 0u;
+                    }
+            }
+            if (s == 0) {
+#pragma unroll
+                for (int q = 0; q < kRowsPerThread; ++q)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[q][k] = g[q][k];
+            } else {
+#pragma unroll
+                for (int q = 0; q < kRowsPerThread; ++q) {
+                    if (r23[q].x == 1.0 && r23[q].y == 1.0) {  // outside the blend band: exact byte add
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[q][k] = __vadd4(v[q][k], g[q][k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[q][k] = blend_px_weighted(v[q][k], r23[q].x, g[q][k], r23[q].y);
+                    }
+                }
+            }
+        }
+
+        const unsigned o = out_sa + b * kOutTileBytes;
+#pragma unroll
+        for (int q = 0; q < kRowsPerThread; ++q) store_quad_sa(o + q * kRowGroups * kOutRowBytes, v[q]);
+        ptx::fence_async_smem();
+        if (tid < NSLOT) ring[((it + 3) & 3) * 2 + tid] = pre;
+        if (tid == 0) ptx::bulk_wait_read0();  // the store of the previous tile has left the other output tile
+        __syncthreads();
+        if (tid == 0) {
+            if (u + 2 * G < n_tiles) issue((it + 2) & 3, b);
+            ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, y0, 0, out_tiles + b * kOutTileBytes, drop);
+            ptx::bulk_commit();
+        }
+    }
+    if (tid == 0) ptx::bulk_wait_read0();
+}
+
+inline int sep1_smem_bytes(int cap) { return 2 * kOutTileBytes + 2 * (128 + cap) + 8 * (int)sizeof(int4) + 16 + 128; }
+
+}  // namespace pb

@@ -84,6 +84,8 @@ struct TiledArgs {
     int debug;  // timing experiments (wrong output): 1 = no loads / waits, 2 = no gather, 4 = no stores
 #endif
     const int4* tile_fp;  // separable: per (tile, slot) footprint {by0, xb0, nbox, all_valid | need_bytes << 1}
+    const int4* sep1_tab; // separable: the same per (tile in launch order, slot), pre-decoded (pb_sep1.cuh)
+    int sep1_cap;         // single-frame kernel: capacity of one stage buffer, bytes (multiple of 128)
 };
 
 // footprint census written by a probe launch: how many (tile, slot) items need a stage buffer of
