@@ -3,6 +3,7 @@
 // Build (photonbend_b200/build.py):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
 //        -Xcompiler -fPIC,-ffp-contract=off -shared -Iinclude -o libpbremap.so pb_remap.cu
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -473,7 +474,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // persistent single-frame kernel: as many CTAs as the device holds at once
 template <int SRC_KIND>
 static cudaError_t launch_sep1_one(const TiledArgs& a, cudaStream_t st) {
-    const int smem = sep1_smem_bytes(a.sep1_cap);
+    const int smem = sep1_smem_bytes(a.sep1_cap, SRC_KIND == PB_KIND_DOUBLE);
     static int max_smem_set = 0;
     if (smem > max_smem_set) {
         cudaError_t e = cudaFuncSetAttribute(remap_sep1_kernel<SRC_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -559,11 +560,21 @@ static int footprint_entries(const pb_plan& p) {
 }
 // col_tab [W][2] + row_tab [H][4] doubles, then one int4 footprint per (tile, slot), then the same
 // per (tile in launch order, slot) for the single-frame kernel
+static size_t sep1_row_doubles(const pb_plan& p) { return p.src.kind == PB_KIND_DOUBLE ? 4 : 1; }
 static size_t table_doubles(const pb_plan& p) {
-    return 2 * (size_t)p.out.W + 4 * (size_t)p.out.H + 4 * (size_t)footprint_entries(p);
+    return 2 * (size_t)p.out.W + 4 * (size_t)p.out.H + 4 * (size_t)footprint_entries(p) +
+           2 * (size_t)tiles_x(p) * kTileW + sep1_row_doubles(p) * (size_t)tiles_y(p) * kTileH;
 }
 static const int4* sep1_table(const pb_plan& p, const double* tables) {
     return reinterpret_cast<const int4*>(tables + 2 * (size_t)p.out.W + 4 * (size_t)p.out.H) + footprint_entries(p);
+}
+// (W and H need not be even: the int4 tables keep everything after them 16-byte aligned only if
+// 2W + 4H is even, which it is)
+static const double* sep1_col(const pb_plan& p, const double* tables) {
+    return tables + 2 * (size_t)p.out.W + 4 * (size_t)p.out.H + 4 * (size_t)footprint_entries(p);
+}
+static const double* sep1_row(const pb_plan& p, const double* tables) {
+    return sep1_col(p, tables) + 2 * (size_t)tiles_x(p) * kTileW;
 }
 static const int4* footprint_table(const pb_plan& p, const double* tables) {
     return reinterpret_cast<const int4*>(tables + 2 * (size_t)p.out.W + 4 * (size_t)p.out.H);
@@ -709,6 +720,13 @@ static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st
                                                               const_cast<int4*>(sep1_table(p, tables)), tiles_x(p),
                                                               tiles_y(p), p.raster_band,
                                                               p.src.kind == PB_KIND_DOUBLE ? 2 : 1);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int n_slice = std::max(tiles_x(p) * kTileW, tiles_y(p) * kTileH);
+    pb_sep1_slices_kernel<<<(n_slice + 255) / 256, 256, 0, st>>>(tables, tables + 2 * (size_t)p.out.W,
+                                                               const_cast<double*>(sep1_col(p, tables)),
+                                                               const_cast<double*>(sep1_row(p, tables)), p.out.W, p.out.H,
+                                                               tiles_x(p), tiles_y(p), (int)sep1_row_doubles(p));
     return cudaGetLastError();
 }
 
@@ -732,6 +750,8 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         a.row_tab = tables ? tables + 2 * (size_t)p.out.W : nullptr;
         a.tile_fp = tables ? footprint_table(p, tables) : nullptr;
         a.sep1_tab = tables ? sep1_table(p, tables) : nullptr;
+        a.sep1_col = tables ? sep1_col(p, tables) : nullptr;
+        a.sep1_row = tables ? sep1_row(p, tables) : nullptr;
         a.sep1_cap = p.sep1_cap;
         a.src_px = src;
         a.src_frame_stride = src_frame_stride;

@@ -57,10 +57,36 @@ __global__ void __launch_bounds__(256) pb_sep1_table_kernel(const int4* __restri
     }
 }
 
+// Per-tile table slices for the single-frame kernel, laid out so that ONE bulk copy brings a tile's
+// slice into shared memory and the threads' reads of it are conflict-free:
+//   col: tiles_x x 32 entries (cos, sin); column c of a tile sits at (c & 3) * 8 + (c >> 2), so the
+//        eight quad columns of a warp read 128 contiguous bytes for each of their 4 columns;
+//   row: tiles_y x 64 entries; camera: lens radius (8 bytes); double: (radius left, radius right,
+//        weight left, weight right) (32 bytes).
+// Entries past the image edge repeat the last column / row (their pixels are clipped by the store).
+__global__ void __launch_bounds__(256) pb_sep1_slices_kernel(const double* __restrict__ col_tab,
+                                                             const double* __restrict__ row_tab, double* __restrict__ col_out,
+                                                             double* __restrict__ row_out, int W, int H, int tiles_x,
+                                                             int tiles_y, int row_doubles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < tiles_x * kTileW) {
+        const int c = t & (kTileW - 1);
+        const int j = min(t, W - 1);
+        double* o = col_out + 2 * ((t - c) + (c & 3) * 8 + (c >> 2));
+        o[0] = col_tab[2 * j];
+        o[1] = col_tab[2 * j + 1];
+    }
+    if (t < tiles_y * kTileH) {
+        const int i = min(t, H - 1);
+        for (int e = 0; e < row_doubles; ++e) row_out[(size_t)t * row_doubles + e] = row_tab[4 * i + e];
+    }
+}
+
 struct Sep1Slot {
-    int nbox, pitch, rect, by0, xb0, origin;
+    int nbox, pitch, rect, by0, xb0, origin, tile;
     bool all_valid;
     __device__ __forceinline__ void decode(const int4 d) {
+        tile = d.z;
         nbox = (d.x >> 16) & 0xff;
         pitch = ((d.x >> 24) & 0x3f) << 4;
         rect = nbox * kBoxRows * pitch;
@@ -78,9 +104,13 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
     constexpr int NSLOT = DBL ? 2 : 1;
 
     extern __shared__ __align__(128) unsigned char smem[];
-    // [ out tile 0 ][ out tile 1 ][ stage 0: 128 zero bytes + cap ][ stage 1 ][ ring of 4 tile descriptors ][ 2 mbarriers ]
+    // [ out tile 0 ][ out tile 1 ][ stage 0 ][ stage 1 ][ ring of 4 tile descriptors ][ 2 mbarriers ]
+    // stage buffer: [128 zero bytes][column slice 512][row slice 512 | 2048][source rectangles, up to cap bytes]
+    constexpr int kColBytes = kTileW * 16;
+    constexpr int kRowBytes = kTileH * (DBL ? 32 : 8);
+    constexpr int kHead = 128 + kColBytes + kRowBytes;  // rectangles start here (a multiple of 128)
     const int cap = a.sep1_cap;
-    const int buf_bytes = 128 + cap;
+    const int buf_bytes = kHead + cap;
     unsigned char* out_tiles = smem;
     unsigned char* stages = smem + 2 * kOutTileBytes;
     int4* ring = reinterpret_cast<int4*>(stages + 2 * buf_bytes);
@@ -112,11 +142,16 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
         Sep1Slot s0, s1;
         s0.decode(ring[r * 2]);
         s1.decode(DBL ? ring[r * 2 + 1] : make_int4(0, 0, 0, 0));
-        const int total = s0.rect + s1.rect;
-        if (total == 0 || total > cap) return;  // nothing visible, or gathered from global memory
-        ptx::mbarrier_arrive_expect_tx(&bars[b], (unsigned)total);
+        const int tx = s0.tile & 0xffff, ty = s0.tile >> 16;
+        int total = s0.rect + s1.rect;
+        if (total > cap) total = 0;  // gathered from global memory: only the table slices are staged
+        ptx::mbarrier_arrive_expect_tx(&bars[b], (unsigned)(total + kColBytes + kRowBytes));
+        unsigned char* head = stages + b * buf_bytes + 128;
+        ptx::bulk_g2s(head, a.sep1_col + (size_t)tx * (kColBytes / 8), kColBytes, &bars[b]);
+        ptx::bulk_g2s(head + kColBytes, a.sep1_row + (size_t)ty * (kRowBytes / 8), kRowBytes, &bars[b]);
+        if (total == 0) return;
         const uint64_t keep = ptx::policy_evict_last();
-        unsigned char* base = stages + b * buf_bytes + 128;
+        unsigned char* base = stages + b * buf_bytes + kHead;
         if (s0.nbox > 0) {
             const CUtensorMap* map = &a.src_maps[(s0.pitch >> 5) - (kMinStageUnits >> 1)];
             for (int k = 0; k < s0.nbox; ++k)
@@ -156,25 +191,29 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
         const int total = sl[0].rect + sl[1].rect;
         const bool staged = total <= cap;  // block-uniform
 
-        // tables: 4 columns, 2 rows per thread (rows / columns past the image edge repeat the last one: TMA clips them)
-        const int jx = x0 + 4 * qc;
+        ptx::mbarrier_wait_sa(ptx::smem_addr(&bars[b]), (phase >> b) & 1u);
+        phase ^= 1u << b;
+        const unsigned stage_sa = stages_sa + b * buf_bytes;
+        const unsigned char* __restrict__ frame = a.src_px;
+
+        // table slices: 4 columns, 2 rows per thread
+        const unsigned char* head = stages + b * buf_bytes + 128;
         double2 cs[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cs[k] = __ldg(reinterpret_cast<const double2*>(a.col_tab) + min(jx + k, a.out.W - 1));
+        for (int k = 0; k < 4; ++k) cs[k] = reinterpret_cast<const double2*>(head)[k * 8 + qc];
         double2 r01[kRowsPerThread], r23[kRowsPerThread];
 #pragma unroll
         for (int q = 0; q < kRowsPerThread; ++q) {
-            const int i = min(y0 + rg + q * kRowGroups, a.out.H - 1);
-            r01[q] = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i);
-            if (DBL) r23[q] = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i + 1);
+            const int r = rg + q * kRowGroups;
+            if (DBL) {
+                r01[q] = reinterpret_cast<const double2*>(head + kColBytes)[2 * r];
+                r23[q] = reinterpret_cast<const double2*>(head + kColBytes)[2 * r + 1];
+            } else {
+                r01[q].x = reinterpret_cast<const double*>(head + kColBytes)[r];
+                r01[q].y = 0.0;
+                r23[q] = make_double2(1.0, 1.0);
+            }
         }
-
-        if (staged && total > 0) {
-            ptx::mbarrier_wait_sa(ptx::smem_addr(&bars[b]), (phase >> b) & 1u);
-            phase ^= 1u << b;
-        }
-        const unsigned stage_sa = stages_sa + b * buf_bytes;
-        const unsigned char* __restrict__ frame = a.src_px;
 
         // v[q][k]: the pixel (low 3 bytes) of row q, column k of this thread
         unsigned v[kRowsPerThread][4];
@@ -191,7 +230,7 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
                     for (int k = 0; k < 4; ++k) g[q][k] = 0u;
             } else if (staged) {
                 // byte offset inside the stage buffer = py * pitch + px * 3 + (128 + rectangle start - origin)
-                const int base = 128 + (s ? sl[0].rect : 0) - S.origin;
+                const int base = kHead + (s ? sl[0].rect : 0) - S.origin;
                 if (S.all_valid) {
 #pragma unroll
                     for (int q = 0; q < kRowsPerThread; ++q)
@@ -267,6 +306,9 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
     if (tid == 0) ptx::bulk_wait_read0();
 }
 
-inline int sep1_smem_bytes(int cap) { return 2 * kOutTileBytes + 2 * (128 + cap) + 8 * (int)sizeof(int4) + 16 + 128; }
+inline int sep1_smem_bytes(int cap, bool dbl) {
+    const int head = 128 + kTileW * 16 + kTileH * (dbl ? 32 : 8);
+    return 2 * kOutTileBytes + 2 * (head + cap) + 8 * (int)sizeof(int4) + 16 + 128;
+}
 
 }  // namespace pb

@@ -85,7 +85,9 @@ struct TiledArgs {
 #endif
     const int4* tile_fp;  // separable: per (tile, slot) footprint {by0, xb0, nbox, all_valid | need_bytes << 1}
     const int4* sep1_tab; // separable: the same per (tile in launch order, slot), pre-decoded (pb_sep1.cuh)
-    int sep1_cap;         // single-frame kernel: capacity of one stage buffer, bytes (multiple of 128)
+    const double* sep1_col;  // single-frame kernel: per-tile column / row table slices (pb_sep1_slices_kernel)
+    const double* sep1_row;
+    int sep1_cap;         // single-frame kernel: bytes of source rectangles one stage buffer holds (multiple of 128)
 };
 
 // footprint census written by a probe launch: how many (tile, slot) items need a stage buffer of
