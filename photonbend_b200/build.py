@@ -30,6 +30,11 @@ NVCC_FLAGS = [
 ]
 
 
+IO_LIB_PATH = os.path.join(PKG, "libpbio.so")
+IO_SOURCE = os.path.join(CSRC, "pb_io.cpp")
+IO_HEADER = os.path.join(REPO, "include", "pb_io.h")
+
+
 def find_nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -61,5 +66,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def io_is_stale() -> bool:
+    if not os.path.exists(IO_LIB_PATH):
+        return True
+    built = os.path.getmtime(IO_LIB_PATH)
+    return any(os.path.getmtime(p) > built for p in (IO_SOURCE, IO_HEADER))
+
+
+def build_io(force: bool = False) -> str:
+    """libpbio.so: the nvJPEG bridge (host C++, no kernels of its own)."""
+    if not force and not io_is_stale():
+        return IO_LIB_PATH
+    cuda = os.path.dirname(os.path.dirname(find_nvcc()))
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-I", os.path.join(cuda, "include"),
+           "-I", os.path.join(REPO, "include"), IO_SOURCE, "-L", os.path.join(cuda, "lib64"),
+           "-lnvjpeg", "-lcudart", "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", IO_LIB_PATH]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("building libpbio.so failed:\n" + proc.stdout + proc.stderr)
+    return IO_LIB_PATH
+
+
 if __name__ == "__main__":
+    print(build_io(force="--force" in sys.argv))
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

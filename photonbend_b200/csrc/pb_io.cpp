@@ -1,0 +1,171 @@
+// pb_io.cpp -- libpbio.so: JPEG <-> device uint8 HWC tensors through nvJPEG (see include/pb_io.h).
+//
+// Build (photonbend_b200/build.py):  g++ -O2 -fPIC -shared -I<cuda>/include -Iinclude pb_io.cpp
+//                                        -L<cuda>/lib64 -lnvjpeg -lcudart -o libpbio.so
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include <cuda_runtime.h>
+#include <nvjpeg.h>
+
+#include "pb_io.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+
+const char* status_name(nvjpegStatus_t s) {
+    switch (s) {
+        case NVJPEG_STATUS_NOT_INITIALIZED: return "not initialized";
+        case NVJPEG_STATUS_INVALID_PARAMETER: return "invalid parameter";
+        case NVJPEG_STATUS_BAD_JPEG: return "bad jpeg";
+        case NVJPEG_STATUS_JPEG_NOT_SUPPORTED: return "jpeg not supported";
+        case NVJPEG_STATUS_ALLOCATOR_FAILURE: return "allocator failure";
+        case NVJPEG_STATUS_EXECUTION_FAILED: return "execution failed";
+        case NVJPEG_STATUS_ARCH_MISMATCH: return "arch mismatch";
+        case NVJPEG_STATUS_INTERNAL_ERROR: return "internal error";
+        case NVJPEG_STATUS_IMPLEMENTATION_NOT_SUPPORTED: return "implementation not supported";
+        default: return "unknown status";
+    }
+}
+
+int codec_fail(nvjpegStatus_t s, const char* what) {
+    return fail(s == NVJPEG_STATUS_JPEG_NOT_SUPPORTED || s == NVJPEG_STATUS_IMPLEMENTATION_NOT_SUPPORTED
+                    ? PB_IO_ERR_UNSUPPORTED
+                    : PB_IO_ERR_CODEC,
+                std::string(what) + ": nvjpeg " + status_name(s));
+}
+
+// one handle, one decoder state and one encoder state per process, serialised by a mutex: the
+// callers (CLI commands, a frame loop) decode / encode one image at a time
+struct Codec {
+    std::mutex lock;
+    nvjpegHandle_t handle = nullptr;
+    nvjpegJpegState_t dec_state = nullptr;
+    nvjpegEncoderState_t enc_state = nullptr;
+    nvjpegEncoderParams_t enc_params = nullptr;
+    bool tried = false;
+    nvjpegStatus_t init_status = NVJPEG_STATUS_NOT_INITIALIZED;
+
+    nvjpegStatus_t ensure() {
+        if (tried) return init_status;
+        tried = true;
+        init_status = nvjpegCreateSimple(&handle);
+        if (init_status == NVJPEG_STATUS_SUCCESS) init_status = nvjpegJpegStateCreate(handle, &dec_state);
+        return init_status;
+    }
+    nvjpegStatus_t ensure_encoder(cudaStream_t st) {
+        if (enc_state) return NVJPEG_STATUS_SUCCESS;
+        nvjpegStatus_t s = nvjpegEncoderStateCreate(handle, &enc_state, st);
+        if (s == NVJPEG_STATUS_SUCCESS) s = nvjpegEncoderParamsCreate(handle, &enc_params, st);
+        return s;
+    }
+};
+
+Codec& codec() {
+    static Codec c;  // never destroyed: the CUDA context may already be gone at exit
+    return c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pb_io_version(void) { return 1; }
+
+const char* pb_io_last_error(void) { return g_error.c_str(); }
+
+int pb_io_jpeg_info(const uint8_t* jpeg, size_t jpeg_bytes, int32_t* width, int32_t* height, int32_t* components) {
+    if (!jpeg || jpeg_bytes == 0 || !width || !height || !components)
+        return fail(PB_IO_ERR_INVALID_ARGUMENT, "pb_io_jpeg_info: null pointer or empty buffer");
+    Codec& c = codec();
+    std::lock_guard<std::mutex> guard(c.lock);
+    nvjpegStatus_t s = c.ensure();
+    if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_info (nvjpeg start-up)");
+    int n = 0, widths[NVJPEG_MAX_COMPONENT] = {0}, heights[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t css;
+    s = nvjpegGetImageInfo(c.handle, jpeg, jpeg_bytes, &n, &css, widths, heights);
+    if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_info");
+    *width = widths[0];
+    *height = heights[0];
+    *components = n;
+    return PB_IO_OK;
+}
+
+int pb_io_jpeg_decode_rgb_u8(const uint8_t* jpeg, size_t jpeg_bytes, uint8_t* dst, int32_t width, int32_t height,
+                             void* stream) {
+    if (!jpeg || jpeg_bytes == 0 || !dst)
+        return fail(PB_IO_ERR_INVALID_ARGUMENT, "pb_io_jpeg_decode_rgb_u8: null pointer or empty buffer");
+    if (width < 1 || height < 1) return fail(PB_IO_ERR_INVALID_ARGUMENT, "pb_io_jpeg_decode_rgb_u8: bad size");
+    Codec& c = codec();
+    std::lock_guard<std::mutex> guard(c.lock);
+    nvjpegStatus_t s = c.ensure();
+    if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_decode_rgb_u8 (nvjpeg start-up)");
+    int n = 0, widths[NVJPEG_MAX_COMPONENT] = {0}, heights[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t css;
+    s = nvjpegGetImageInfo(c.handle, jpeg, jpeg_bytes, &n, &css, widths, heights);
+    if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_decode_rgb_u8");
+    if (widths[0] != width || heights[0] != height)
+        return fail(PB_IO_ERR_INVALID_ARGUMENT, "pb_io_jpeg_decode_rgb_u8: destination size differs from the image's");
+    nvjpegImage_t img;
+    std::memset(&img, 0, sizeof(img));
+    img.channel[0] = dst;
+    img.pitch[0] = (size_t)width * 3;
+    s = nvjpegDecode(c.handle, c.dec_state, jpeg, jpeg_bytes, NVJPEG_OUTPUT_RGBI, &img, (cudaStream_t)stream);
+    if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_decode_rgb_u8");
+    return PB_IO_OK;
+}
+
+int pb_io_jpeg_encode_rgb_u8(const uint8_t* src, int32_t width, int32_t height, int32_t quality, int32_t subsampling,
+                             void* stream, uint8_t* out, size_t* out_bytes) {
+    if (!src || !out_bytes) return fail(PB_IO_ERR_INVALID_ARGUMENT, "pb_io_jpeg_encode_rgb_u8: null pointer");
+    if (width < 1 || height < 1 || width > 65535 || height > 65535)
+        return fail(PB_IO_ERR_INVALID_ARGUMENT, "pb_io_jpeg_encode_rgb_u8: a JPEG is 1..65535 pixels on a side");
+    if (quality < 1 || quality > 100) return fail(PB_IO_ERR_INVALID_ARGUMENT, "pb_io_jpeg_encode_rgb_u8: quality must be 1..100");
+    nvjpegChromaSubsampling_t css;
+    switch (subsampling) {
+        case PB_IO_CSS_444: css = NVJPEG_CSS_444; break;
+        case PB_IO_CSS_422: css = NVJPEG_CSS_422; break;
+        case PB_IO_CSS_420: css = NVJPEG_CSS_420; break;
+        default: return fail(PB_IO_ERR_INVALID_ARGUMENT, "pb_io_jpeg_encode_rgb_u8: unknown subsampling");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Codec& c = codec();
+    std::lock_guard<std::mutex> guard(c.lock);
+    nvjpegStatus_t s = c.ensure();
+    if (s == NVJPEG_STATUS_SUCCESS) s = c.ensure_encoder(st);
+    if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_encode_rgb_u8 (nvjpeg start-up)");
+    s = nvjpegEncoderParamsSetQuality(c.enc_params, quality, st);
+    if (s == NVJPEG_STATUS_SUCCESS) s = nvjpegEncoderParamsSetSamplingFactors(c.enc_params, css, st);
+    if (s == NVJPEG_STATUS_SUCCESS) s = nvjpegEncoderParamsSetOptimizedHuffman(c.enc_params, 0, st);
+    if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_encode_rgb_u8 (parameters)");
+    nvjpegImage_t img;
+    std::memset(&img, 0, sizeof(img));
+    img.channel[0] = const_cast<uint8_t*>(src);
+    img.pitch[0] = (size_t)width * 3;
+    s = nvjpegEncodeImage(c.handle, c.enc_state, c.enc_params, &img, NVJPEG_INPUT_RGBI, width, height, st);
+    if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_encode_rgb_u8");
+    cudaError_t e = cudaStreamSynchronize(st);  // the bitstream is assembled on the host from device results
+    if (e != cudaSuccess) return fail(PB_IO_ERR_CUDA, std::string("pb_io_jpeg_encode_rgb_u8: ") + cudaGetErrorString(e));
+    size_t need = 0;
+    s = nvjpegEncodeRetrieveBitstream(c.handle, c.enc_state, nullptr, &need, st);
+    if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_encode_rgb_u8 (size)");
+    if (!out || *out_bytes < need) {
+        *out_bytes = need;
+        return fail(PB_IO_ERR_INVALID_ARGUMENT, "pb_io_jpeg_encode_rgb_u8: output buffer too small");
+    }
+    s = nvjpegEncodeRetrieveBitstream(c.handle, c.enc_state, out, &need, st);
+    if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_encode_rgb_u8 (bitstream)");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(PB_IO_ERR_CUDA, std::string("pb_io_jpeg_encode_rgb_u8: ") + cudaGetErrorString(e));
+    *out_bytes = need;
+    return PB_IO_OK;
+}
+
+}  // extern "C"

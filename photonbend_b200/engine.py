@@ -156,7 +156,14 @@ def to_device_u8(image):
     if is_torch_tensor(image):
         t = image
     else:
-        t = torch.from_numpy(np.ascontiguousarray(image))
+        arr = np.ascontiguousarray(image)
+        if not arr.flags.writeable:  # e.g. np.asarray(PIL image): read-only view, only ever read here
+            arr = arr.view()
+            try:
+                arr.flags.writeable = True
+            except ValueError:
+                arr = arr.copy()
+        t = torch.from_numpy(arr)
     if not t.is_cuda:
         t = t.to("cuda", non_blocking=True)
     return t.contiguous()

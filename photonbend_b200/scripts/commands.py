@@ -28,12 +28,11 @@ from typing import List, Optional, Tuple
 
 import click
 import numpy as np
-from PIL import Image
 
 from photonbend_b200.core import lens as lenses
 from photonbend_b200.core.projection import CameraImage, DoubleCameraImage, PanoramaImage
 from photonbend_b200.core.rotation import Rotation
-from photonbend_b200.utils import to_radians
+from photonbend_b200.utils import image_io, to_radians
 
 CHANNELS = 3
 IMAGE_TYPES = ("inscribed", "double", "cropped", "full")
@@ -77,19 +76,20 @@ def _checked_output(path: Path) -> Path:
     return path
 
 
-def _load_pixels(path) -> np.ndarray:
+def _load_pixels(path):
+    """uint8 pixels of the input file: a NumPy array (Pillow, the default) or, with
+    PHOTONBEND_B200_CODEC=nvjpeg, a CUDA tensor decoded on the device (utils/image_io.py)."""
     try:
-        with Image.open(path) as img:
-            return np.asarray(img)
+        return image_io.open_image(path)
     except IOError:
         print("Error: Input image could not be opened!")
         print("Exiting!")
         sys.exit(1)
 
 
-def _save_pixels(pixels: np.ndarray, path: Path) -> None:
+def _save_pixels(pixels, path: Path) -> None:
     try:
-        Image.fromarray(np.ascontiguousarray(pixels)).save(path)
+        image_io.save_image(pixels, path)
     except IOError:
         print("Could not save to the specified location!")
         print("Exiting!")

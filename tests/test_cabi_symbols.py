@@ -67,3 +67,53 @@ def test_argument_errors_need_no_gpu():
     handle = ctypes.c_void_p()
     assert lib.pb_plan_create(None, None, ctypes.byref(handle)) == _native.PB_ERR_INVALID_ARGUMENT
     lib.pb_plan_destroy(None)  # destroying nothing is allowed
+
+
+# ------------------------------------------------------------------ libpbio.so (include/pb_io.h)
+
+
+def _declared_io_functions():
+    with open(os.path.join(REPO, "include", "pb_io.h")) as fh:
+        text = fh.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb_io_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_io_header_binding_and_library_agree():
+    from photonbend_b200.utils import image_io
+
+    declared = _declared_io_functions()
+    assert declared and sorted(image_io.EXPORTS) == declared
+    lib = image_io.load_codec()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pb_io_version() == 1
+
+
+def test_io_argument_errors_need_no_gpu():
+    from photonbend_b200.utils import image_io
+
+    lib = image_io.load_codec()
+    w, h, n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    assert lib.pb_io_jpeg_info(None, 0, ctypes.byref(w), ctypes.byref(h), ctypes.byref(n)) == image_io.PB_IO_ERR_INVALID_ARGUMENT
+    assert b"null" in lib.pb_io_last_error()
+    size = ctypes.c_size_t(0)
+    fake = ctypes.c_void_p(256)  # never dereferenced: validation fails first
+    assert lib.pb_io_jpeg_encode_rgb_u8(fake, 0, 10, 75, 2, None, None, ctypes.byref(size)) == image_io.PB_IO_ERR_INVALID_ARGUMENT
+    assert lib.pb_io_jpeg_encode_rgb_u8(fake, 10, 10, 0, 2, None, None, ctypes.byref(size)) == image_io.PB_IO_ERR_INVALID_ARGUMENT
+    assert b"quality" in lib.pb_io_last_error()
+    assert lib.pb_io_jpeg_encode_rgb_u8(fake, 10, 10, 75, 9, None, None, ctypes.byref(size)) == image_io.PB_IO_ERR_INVALID_ARGUMENT
+    assert lib.pb_io_jpeg_decode_rgb_u8(None, 0, None, 1, 1, None) == image_io.PB_IO_ERR_INVALID_ARGUMENT
+
+
+def test_codec_selection(monkeypatch):
+    import pytest
+    from photonbend_b200.utils import image_io
+
+    monkeypatch.delenv("PHOTONBEND_B200_CODEC", raising=False)
+    assert image_io.selected_codec() == "pil"
+    monkeypatch.setenv("PHOTONBEND_B200_CODEC", "NVJPEG")
+    assert image_io.selected_codec() == "nvjpeg"
+    monkeypatch.setenv("PHOTONBEND_B200_CODEC", "turbo")
+    with pytest.raises(ValueError):
+        image_io.selected_codec()
