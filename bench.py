@@ -342,7 +342,7 @@ def quick_kernel_rate(torch, name, frames, steps=20, warmup=3):
     return {"title": wl["title"], "frames_per_launch": frames, "value": px / (total_ms / steps * 1e-3) / 1e9,
             "unit": UNIT, "ms_per_launch": avg_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak}}
+                         "frac": achieved / peak, "traffic": committed_traffic(name, frames)}}
 
 
 def run_gpu(args):
@@ -413,9 +413,9 @@ def run_gpu(args):
 
     also = {}
     if world == 1 and not args.no_also:
-        for other, fr in (("T", frames), ("cfg1", 1), ("cfg2", 1), ("cfg3", 1), ("cfg4", 1)):
+        for other, fr in (("T", frames), ("T", 1), ("cfg1", 1), ("cfg2", 1), ("cfg3", 1), ("cfg4", 1)):
             if other != name:
-                also[other] = quick_kernel_rate(torch, other, fr)
+                also[other if (fr == 1) == (other != "T") else f"{other}_{fr}frame"] = quick_kernel_rate(torch, other, fr)
 
     if rank == 0:
         line = {

@@ -489,7 +489,8 @@ static cudaError_t launch_sep1_one(const TiledArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     int grid = sms * per_sm;
-    if (const char* env = std::getenv("PB_SEP1_GRID")) grid = std::atoi(env);  // tuning experiments
+    if (const char* env = std::getenv("PB_SEP1_WAVES")) grid *= std::atoi(env);  // tuning experiments
+    if (const char* env = std::getenv("PB_SEP1_GRID")) grid = std::atoi(env);
     const int n_tiles = a.tiles_x * a.tiles_y;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
@@ -765,6 +766,8 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         // (8K target) or harmful (double source, -8 %), so it is off  (gpurun_out/run3.log, run12.log)
         a.l2_ahead = 0;
         if (const char* e = std::getenv("PB_L2_AHEAD")) a.l2_ahead = std::atoi(e);  // tuning experiments
+        a.lean_min_groups = 1;
+        if (const char* e = std::getenv("PB_LEAN_MIN_GROUPS")) a.lean_min_groups = std::atoi(e);  // tuning experiments
 #ifdef PB_EXPERIMENTS
         if (const char* e = std::getenv("PB_DEBUG_MODE")) a.debug = std::atoi(e);
 #endif

@@ -295,15 +295,19 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
         for (int q = 0; q < kRowsPerThread; ++q) store_quad_sa(o + q * kRowGroups * kOutRowBytes, v[q]);
         ptx::fence_async_smem();
         if (tid < NSLOT) ring[((it + 3) & 3) * 2 + tid] = pre;
-        if (tid == 0) ptx::bulk_wait_read0();  // the store of the previous tile has left the other output tile
+        // The loads of tile it + 2 and the store of this tile are issued by lane 0 of warp (it mod 8):
+        // rotating the duty spreads its cost over the warps instead of making one warp late at
+        // every barrier.  Bulk async-groups belong to the issuing thread, so the thread that
+        // stored the previous tile waits for that store to have left the other output tile.
+        if (tid == (((it - 1) & 7) << 5) && it > 0) ptx::bulk_wait_read0();
         __syncthreads();
-        if (tid == 0) {
+        if (tid == ((it & 7) << 5)) {
             if (u + 2 * G < n_tiles) issue((it + 2) & 3, b);
             ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, y0, 0, out_tiles + b * kOutTileBytes, drop);
             ptx::bulk_commit();
         }
     }
-    if (tid == 0) ptx::bulk_wait_read0();
+    if ((tid & 31) == 0) ptx::bulk_wait_read0();  // every issuing thread: its stores have left shared memory
 }
 
 inline int sep1_smem_bytes(int cap, bool dbl) {

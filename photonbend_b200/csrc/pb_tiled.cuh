@@ -78,6 +78,7 @@ struct TiledArgs {
     int n_out;        // output tile buffers: 1, or 2 (the store of frame f overlaps frame f+1)
     int* probe;       // non-null: footprint census only (see pb_plan_create), nothing is remapped
     int tiles_x, tiles_y;  // tiles per output row / column
+    int lean_min_groups;  // tiles that cannot keep this many frames in flight use the (frame, slot) item loop
     int l2_ahead;     // items whose boxes are prefetched into L2 ahead of the shared-memory loads
     int raster_band;  // CTAs walk bands of this many tile rows column by column (0: plain row-major)
 #ifdef PB_EXPERIMENTS
@@ -587,7 +588,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 #ifdef PB_EXPERIMENTS
     if (a.debug >> 8) n_groups = min(n_groups, a.debug >> 8);
 #endif
-    const bool lean = unit_weights && n_act >= 1 && n_groups >= 1 &&
+    const bool lean = unit_weights && n_act >= 1 && n_groups >= a.lean_min_groups &&
                       (a.n_out == 2 || a.n_frames == 1) && !dbg_noload && !dbg_nogather && !dbg_nostore;
     auto issue_group = [&](int f, int g) {  // one thread: every rectangle of frame f into group g
         unsigned char* base = stages + g * group_bytes + 128;

@@ -281,6 +281,14 @@ def test_tiled_fast_path_mid_size_batches(torch_cuda, src_kind):
         helpers.product_map(og, ())).cpu().numpy()
     for k in range(3):
         assert np.array_equal(out[k], numpy_port.remap(og, (), sg, frames[k])), (src_kind, k)
+    # one frame per launch: the persistent single-frame kernel (csrc/pb_sep1.cuh), partial edge tiles
+    single = helpers.product_remap(og, (), sg, frames[1])
+    assert np.array_equal(single, out[1]), src_kind
+    # ... and with fewer tiles than resident CTAs, odd tile counts, a one-tile image
+    for oh, ow in ((64, 32), (48, 80), (200, 1040), (65, 48)):
+        og2 = {"kind": "equirect", "height": oh, "width": ow}
+        assert np.array_equal(helpers.product_remap(og2, (), sg, frames[2]), numpy_port.remap(og2, (), sg, frames[2])), \
+            (src_kind, oh, ow)
     # same geometry rotated: generic rays through the same tiled memory path
     rots = [(0.3, -0.7, 1.1)]
     got = helpers.product_remap(og, rots, sg, frames[0])
