@@ -183,39 +183,60 @@ def c_port_rate(name: str):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs.
+    NVML is initialised in the constructor (it takes longer than a short timed region), and
+    ``start()`` returns only after the first sample is in."""
 
-    def __init__(self, index: int, period: float = 0.02):
+    def __init__(self, index: int, period: float = 0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self._halt = threading.Event()
+        self._first = threading.Event()
         self.error = None
-
-    def run(self):
+        self._nv = self._handle = None
         try:
             import pynvml as nv
 
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
+            self._nv = nv
+            self._handle = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._handle, nv.NVML_CLOCK_SM)
+            self._names = {
                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
             }
-            while not self._halt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, nm in names.items():
-                    if mask & bit:
-                        self.reasons.add(nm)
-                time.sleep(self.period)
         except Exception as exc:  # NVML missing: report it, never fake numbers
             self.error = repr(exc)
+
+    def _sample(self):
+        nv, h = self._nv, self._handle
+        self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for bit, nm in self._names.items():
+            if mask & bit:
+                self.reasons.add(nm)
+
+    def run(self):
+        if self._nv is None:
+            self._first.set()
+            return
+        try:
+            while not self._halt.is_set():
+                self._sample()
+                self._first.set()
+                time.sleep(self.period)
+        except Exception as exc:
+            self.error = repr(exc)
+            self._first.set()
+
+    def start(self):
+        super().start()
+        self._first.wait(timeout=2)
 
     def stop(self):
         self._halt.set()
@@ -253,7 +274,7 @@ def make_device_batch(torch, name, frames, rank):
                          device="cuda", generator=gen)
 
 
-def timed_kernel_steps(torch, source, cmap, batch, out, steps, warmup, dist):
+def timed_kernel_steps(torch, source, cmap, batch, out, steps, warmup, dist, sampler=None):
     from photonbend_b200.batch import remap_batch
 
     for _ in range(warmup):
@@ -262,6 +283,8 @@ def timed_kernel_steps(torch, source, cmap, batch, out, steps, warmup, dist):
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.start()  # clocks are sampled from here to the end of the timed region
     stream = torch.cuda.current_stream()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -334,13 +357,13 @@ def quick_kernel_rate(torch, name, frames, steps=20, warmup=3):
     total_ms, launch_ms = timed_kernel_steps(torch, source, cmap, batch, out, steps, warmup, None)
     info = golden_info(name)
     px = info["out_pixels"] * frames
-    avg_ms = float(np.mean(launch_ms))
+    avg_ms = float(np.median(launch_ms))
     peak, _ = measured_peak_gbs()
     achieved = algorithmic_bytes_per_frame(name) * frames / (avg_ms * 1e-3) / 1e9
     del batch, out
     torch.cuda.empty_cache()
-    return {"title": wl["title"], "frames_per_launch": frames, "value": px / (total_ms / steps * 1e-3) / 1e9,
-            "unit": UNIT, "ms_per_launch": avg_ms,
+    return {"title": wl["title"], "frames_per_launch": frames, "value": px / (avg_ms * 1e-3) / 1e9,
+            "unit": UNIT, "ms_per_launch": avg_ms, "statistic": "median of 20 launches",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": committed_traffic(name, frames)}}
 
@@ -383,8 +406,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
 
     sampler = ClockSampler(physical_gpu_index(local_rank))
-    sampler.start()
-    total_ms, launch_ms = timed_kernel_steps(torch, source, cmap, batch, out, args.steps, args.warmup, dist)
+    total_ms, launch_ms = timed_kernel_steps(torch, source, cmap, batch, out, args.steps, args.warmup, dist, sampler)
     clocks = sampler.stop()
 
     e2e_dt, h2d, d2h, e2e_launches, _, _ = timed_e2e_steps(
@@ -486,7 +508,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(workloads.WORKLOADS))
