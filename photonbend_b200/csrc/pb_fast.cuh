@@ -46,21 +46,80 @@ struct FastGeom {
 
 constexpr double kTwo52 = 4503599627370496.0;
 
+// atan(t) / t as a polynomial in t^2 on |t| <= tan(pi/8): Chebyshev interpolant of degree 8,
+// |t * P(t^2) - atan(t)| < 1e-14 (tests/analysis/atan_fit.py).  In constant memory so that the
+// coefficients are operands of the DFMAs instead of 64-bit immediates built by two UMOVs each.
+__constant__ double kAtanPoly[9] = {0.9999999999999734,  -0.33333333330806103, 0.199999996052076,
+                                    -0.1428569043658466, 0.11110385295384498,  -0.0907839471343116,
+                                    0.07563718994323626, -0.058745523239813566, 0.030663008090113325};
+
+// 1 / d for a normal, finite d: hardware seed (MUFU.RCP64H) + two Newton steps, ~1 ulp
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
+
+// atan2(y, x) with an absolute error < 5e-14 for finite (x, y) with x^2 + y^2 well above zero (the
+// callers guarantee > 1e-8): one reduction to |t| <= tan(pi/8) by a rotation of pi/4 BEFORE the
+// single division, a degree-8 polynomial, three reflections.  The short cut only needs angles to
+// ~1e-10 (its decisions carry a 2^-19 px guard band); libm's correctly-rounded-ish atan2 / acos
+// cost three times as many issue slots.
+// acos(c) for a unit vector's component c with s = sqrt(1 - c^2) > 0 at hand: atan2(s, c) without
+// the reflections of the general case (s >= 0)
+__device__ __forceinline__ double fast_acos_sc(double s, double c) {
+    const double ac = fabs(c);
+    const double mx = fmax(ac, s), mn = fmin(ac, s);
+    const bool big = mn > 0.41421356237309503 * mx;
+    const double t = (big ? mn - mx : mn) * fast_rcp(big ? mn + mx : mx);
+    const double u = t * t;
+    double p = kAtanPoly[8];
+#pragma unroll
+    for (int k = 7; k >= 0; --k) p = fma(p, u, kAtanPoly[k]);
+    double r = fma(t, p, big ? 0.78539816339744831 : 0.0);  // atan(mn / mx)
+    if (s > ac) r = 1.5707963267948966 - r;                  // atan(s / |c|)
+    return (c < 0.0) ? kPi - r : r;
+}
+
+__device__ __forceinline__ double fast_atan2(double y, double x) {
+    const double ax = fabs(x), ay = fabs(y);
+    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    const bool big = mn > 0.41421356237309503 * mx;
+    const double num = big ? mn - mx : mn;
+    const double den = big ? mn + mx : mx;
+    const double t = num * fast_rcp(den);
+    const double u = t * t;
+    double p = kAtanPoly[8];
+#pragma unroll
+    for (int k = 7; k >= 0; --k) p = fma(p, u, kAtanPoly[k]);
+    double r = fma(t, p, big ? 0.78539816339744831 : 0.0);
+    if (ay > ax) r = 1.5707963267948966 - r;
+    if (x < 0.0) r = kPi - r;
+    return (y < 0.0) ? -r : r;
+}
+
 // Index of source coordinate v along an axis of n pixels, under the reference's rule (truncate
-// toward zero, then 0 <= index < n; projection.py:223-231, 254-259):
-// >= 0 the index, -1 outside the image, -2 undecided (within 2^-19 px of an integer, or not finite).
+// toward zero, then 0 <= index < n; projection.py:223-231, 254-259).
 // One FP64 add: |v| + 1.5 * 2^32 lies in [1.5 * 2^32, 2^33) for |v| < 2^31, where one ulp is 2^-20,
 // so the mantissa of the sum is |v| + 2^31 in fixed point with 20 fraction bits.
-__device__ __forceinline__ int fast_index(double v, int n) {
+struct FastIndex {
+    int idx;       // trunc(|v|)
+    bool decided;  // v is finite, |v| < 2^31 and further than 2^-19 from every integer
+    bool inside;   // 0 <= trunc(v) < n
+};
+__device__ __forceinline__ FastIndex fast_index(double v, int n) {
     const double g = __dadd_rn(fabs(v), 6442450944.0);
     const unsigned lo = (unsigned)__double2loint(g), hi = (unsigned)__double2hiint(g);
-    const unsigned frac = lo & 0xFFFFFu;  // rounded to nearest: the true fraction is within half a unit
-    const int idx = (int)(__funnelshift_r(lo, hi, 20) ^ 0x80000000u);
-    const bool finite = (hi - 0x41F80000u) < 0x00080000u;      // |v| < 2^31, not NaN
-    const bool off_boundary = (frac - 2u) < (0x100000u - 3u);  // 2 <= frac <= 2^20 - 2
-    if (!(finite && off_boundary)) return -2;
-    const bool in = (__double2hiint(v) < 0) ? (idx == 0) : (idx < n);  // (-1, 0) truncates to 0
-    return in ? idx : -1;
+    FastIndex r;
+    r.idx = (int)(__funnelshift_r(lo, hi, 20) ^ 0x80000000u);
+    // hi in [0x41F80000, 0x42000000): |v| < 2^31, not NaN; fraction (rounded to nearest 2^-20) in [2, 2^20 - 2]
+    r.decided = ((hi & 0xFFF80000u) == 0x41F80000u) & (((lo & 0xFFFFFu) - 2u) < (0x100000u - 3u));
+    // (-1, 0) truncates to 0: a negative v is inside only with idx == 0
+    r.inside = (unsigned)r.idx < ((__double2hiint(v) < 0) ? 1u : (unsigned)n);
+    return r;
 }
 
 // Unit vector of the ray of output pixel (i, j) before any rotation:
@@ -164,15 +223,13 @@ __device__ __forceinline__ bool lens_needs_angle(int lens) {
     return lens == PB_LENS_EQUIDISTANT || lens == PB_LENS_THOBY;
 }
 
-// One camera sample from (cos lon, sin lon) * dist = (nx, nz) * q: 0 ok, 2 undecided; xy = packed pixel or none.
-__device__ __forceinline__ int fast_camera_xy(double nx, double nz, double q, int h, int w, double cy, double cx,
-                                              int col0, bool flip, int& xy) {
-    const double fx = fma(nx, q, cx);
-    const double fy = fma(-nz, q, cy);
-    const int ix = fast_index(fx, w), iy = fast_index(fy, h);
-    if (ix == -2 || iy == -2) return 2;
-    xy = pack_xy(ix, iy, col0, w, flip);
-    return 0;
+// One camera sample from (cos lon, sin lon) * dist = (nx, nz) * q: false = undecided; xy = packed pixel or none.
+__device__ __forceinline__ bool fast_camera_xy(double nx, double nz, double q, int h, int w, double cy, double cx,
+                                               int col0, bool flip, int& xy) {
+    const FastIndex ix = fast_index(fma(nx, q, cx), w), iy = fast_index(fma(-nz, q, cy), h);
+    const int col = col0 + (flip ? (w - 1 - ix.idx) : ix.idx);
+    xy = (ix.inside & iy.inside) ? ((iy.idx << 16) | col) : kNoPixel;
+    return ix.decided & iy.decided;
 }
 
 // Source lookup of a rotated unit vector; false = undecided.
@@ -184,33 +241,33 @@ __device__ __forceinline__ bool fast_src_lookup(const SrcGeom& s, const FastGeom
     const double h2 = fma(nx, nx, nz * nz);
     if (!(h2 > 1e-8)) return false;  // within 1e-4 rad of a pole: acos / atan2 are ill-conditioned there
     if (SRC_KIND == PB_KIND_EQUIRECT) {
-        const double lat = acos(ny);
-        const double lon = atan2(nz, nx);
-        const int row = fast_index(lat * fg.inv_seg_h, s.H);
-        const int col = fast_index(fma(lon, fg.inv_seg_w, s.half_w), s.W);
-        if (row < 0 || col < 0) return false;  // (a coordinate outside [0, n) wraps: exact chain)
-        L.xy0 = (row << 16) | col;
-        return true;
+        const double lat = fast_acos_sc(h2 * rsqrt(h2), ny);
+        const double lon = fast_atan2(nz, nx);
+        const FastIndex row = fast_index(lat * fg.inv_seg_h, s.H);
+        const FastIndex col = fast_index(fma(lon, fg.inv_seg_w, s.half_w), s.W);
+        L.xy0 = (row.idx << 16) | col.idx;
+        // (a coordinate outside [0, n) wraps around in the reference: exact chain)
+        return row.decided & col.decided & row.inside & col.inside;
     }
     const double inv_h = rsqrt(h2);
     if (SRC_KIND == PB_KIND_CAMERA) {
-        const double theta = lens_needs_angle(s.lens) ? acos(ny) : 0.0;
+        const double theta = lens_needs_angle(s.lens) ? fast_acos_sc(h2 * inv_h, ny) : 0.0;
         double q;
         const int st = fast_lens_q(s.lens, fg, ny, inv_h, theta, q);
         if (st == 2) return false;
         if (st == 1) return true;
-        return fast_camera_xy(nx, nz, q, s.H, s.W, s.cy, s.cx, 0, false, L.xy0) == 0;
+        return fast_camera_xy(nx, nz, q, s.H, s.W, s.cy, s.cx, 0, false, L.xy0);
     }
     // double source (projection.py:408-462): unit weights only, the blend band takes the exact chain
     if (!((ny > fg.ny_band_hi) || (ny < fg.ny_band_lo))) return false;
     const bool ang = lens_needs_angle(s.lens);
-    const double theta = ang ? acos(ny) : 0.0;
+    const double theta = ang ? fast_acos_sc(h2 * inv_h, ny) : 0.0;
     double ql, qr;
     const int sl = fast_lens_q(s.lens, fg, ny, inv_h, theta, ql);
     const int sr = fast_lens_q(s.lens, fg, -ny, inv_h, ang ? kPi - theta : 0.0, qr);
     if (sl == 2 || sr == 2) return false;
-    if (sl == 0 && fast_camera_xy(nx, nz, ql, s.H, s.wl, s.cy, s.cxl, 0, false, L.xy0)) return false;
-    if (sr == 0 && fast_camera_xy(nx, nz, qr, s.H, s.wr, s.cy, s.cxr, s.wl, true, L.xy1)) return false;
+    if (sl == 0 && !fast_camera_xy(nx, nz, ql, s.H, s.wl, s.cy, s.cxl, 0, false, L.xy0)) return false;
+    if (sr == 0 && !fast_camera_xy(nx, nz, qr, s.H, s.wr, s.cy, s.cxr, s.wl, true, L.xy1)) return false;
     return true;
 }
 
