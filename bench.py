@@ -391,6 +391,9 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist_mod
 
+        # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
 

@@ -786,7 +786,9 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
                                 : tiled_smem_bytes<PB_KIND_DOUBLE, 0>(a.stage_bytes, 2, a.n_out);
             else two = mode ? tiled_smem_bytes<PB_KIND_CAMERA, 1>(a.stage_bytes, 2, a.n_out)
                             : tiled_smem_bytes<PB_KIND_CAMERA, 0>(a.stage_bytes, 2, a.n_out);
-            if (two <= 75 * 1024) a.n_buffers = 2;
+            int limit_kib = 75;  // three CTAs per SM
+            if (const char* e = std::getenv("PB_TWO_BUF_LIMIT_KIB")) limit_kib = std::atoi(e);  // tuning experiments
+            if (two <= limit_kib * 1024) a.n_buffers = 2;
         }
         bool maps_ok = true;
         for (int u = kMinStageUnits; u <= a.max_units && maps_ok; u += 2)
