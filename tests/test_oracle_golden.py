@@ -9,12 +9,14 @@
 """
 
 import hashlib
+import json
+import os
 
 import numpy as np
 import pytest
 
 import case_matrix
-from conftest import mismatch_report
+from conftest import GOLDEN, mismatch_report
 from oracle import c_port, numpy_port
 
 
@@ -134,3 +136,26 @@ def test_rectilinear_fov_limit_raises_like_reference(bad_fov_deg):
             "fov": case_matrix.rad(bad_fov_deg), "magnitude": 3.5}
     with pytest.raises(ValueError):
         numpy_port.focal_distance(geom)
+
+
+def test_tiny_and_degenerate_sizes_against_the_reference():
+    """One-pixel / one-row images, odd double widths, non-2:1 panoramas (tests/tiny_matrix.py):
+    both oracles against outputs of the live reference (tests/golden/make_golden_tiny.py)."""
+    import tiny_matrix
+    from oracle import c_port, numpy_port
+
+    with open(os.path.join(GOLDEN, "tiny_cases.json")) as fh:
+        meta = json.load(fh)
+    outputs = np.load(os.path.join(GOLDEN, "tiny_outputs.npz"))
+    n = n_c_diff = 0
+    for cid, og, rots, sg, seed in tiny_matrix.all_cases():
+        assert "raises" not in meta[cid]
+        image = tiny_matrix.case_image(sg, seed)
+        want = outputs[cid]
+        got = numpy_port.remap(og, rots, sg, image)
+        assert got.shape == want.shape and np.array_equal(got, want), cid
+        got_c = c_port.remap(og, rots, sg, image)
+        assert got_c.shape == want.shape
+        n_c_diff += int((got_c != want).any(axis=2).sum())  # glibc libm vs NumPy's SIMD kernels
+        n += 1
+    assert n == 180 and n_c_diff <= 4, n_c_diff
