@@ -274,6 +274,50 @@ __global__ void __launch_bounds__(256) remap_generic_kernel(const __grid_constan
     }
 }
 
+// ONE frame, any geometry (rotated remaps above all): every thread resolves two quads of four
+// consecutive pixels and gathers them straight from global memory -- no staging, no barrier.
+// With a single frame the resolve (~150+ float64-heavy instructions per pixel even through the
+// short cut) is all that matters: the tiled kernel's two-phase structure (resolve -> shared memory
+// -> footprint -> TMA stage -> gather) costs ~85 instructions per pixel on top and buys nothing,
+// because a warp's 32 byte-gathers of a smooth mapping touch only 8-12 sectors that mostly hit L1
+// (measured: cfg2 153 -> 142 us even with the one-pixel-per-thread generic kernel).
+// C = 3, W % 4 == 0, dst 4-byte aligned: a quad is 12 contiguous bytes = three aligned words.
+template <int OUT_KIND, int SRC_KIND>
+__global__ void __launch_bounds__(256, 3) remap_direct_kernel(const __grid_constant__ RemapArgs a) {
+    constexpr bool DBL = (SRC_KIND == PB_KIND_DOUBLE);
+    const int tid = threadIdx.x;
+    const int j0 = blockIdx.x * kTileW + 4 * (tid & 7);
+    if (j0 >= a.out.W) return;
+    const unsigned char* __restrict__ sp = a.src_px;
+    const int src_pitch = a.src.W * 3;
+#pragma unroll 1
+    for (int q = 0; q < 2; ++q) {
+        const int i = blockIdx.y * kTileH + (tid >> 3) + q * 32;
+        if (i >= a.out.H) break;
+        unsigned long long lo = 0;  // bytes 0..7 of the quad
+        unsigned hi = 0;            // bytes 8..11
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const Lookup L = resolve_lookup<OUT_KIND, SRC_KIND>(a.out, a.fast, a.rot, a.src, i, j0 + k);
+            unsigned px = 0;
+            if (L.xy0 >= 0) px = pick_px_global(sp, (L.xy0 >> 16) * src_pitch + (L.xy0 & 0xffff) * 3);
+            if (DBL) {
+                unsigned p1 = 0;
+                if (L.xy1 >= 0) p1 = pick_px_global(sp, (L.xy1 >> 16) * src_pitch + (L.xy1 & 0xffff) * 3);
+                px = blend_px(px, L.w0, p1, L.w1) & 0xffffffu;
+            }
+            const int sh = 24 * k;  // pixel k sits at bytes 3k .. 3k+2
+            if (k < 3) lo |= (unsigned long long)px << sh;
+            if (k == 2) hi |= px >> 16;
+            if (k == 3) hi |= px << 8;
+        }
+        unsigned* o = reinterpret_cast<unsigned*>(a.dst_px + ((long long)i * a.out.W + j0) * 3);
+        o[0] = (unsigned)lo;
+        o[1] = (unsigned)(lo >> 32);
+        o[2] = hi;
+    }
+}
+
 // get_coordinate_map() + n rotations, materialised.
 template <int OUT_KIND>
 __global__ void __launch_bounds__(256) materialize_map_kernel(const __grid_constant__ OutGeom out,
@@ -370,6 +414,24 @@ static void launch_generic_s(const RemapArgs& a, cudaStream_t st) {
         case PB_KIND_CAMERA: launch_generic_c<OUT_KIND, PB_KIND_CAMERA>(a, st); break;
         case PB_KIND_DOUBLE: launch_generic_c<OUT_KIND, PB_KIND_DOUBLE>(a, st); break;
         default: launch_generic_c<OUT_KIND, PB_KIND_EQUIRECT>(a, st); break;
+    }
+}
+
+template <int OUT_KIND>
+static void launch_direct_s(const RemapArgs& a, dim3 grid, cudaStream_t st) {
+    switch (a.src.kind) {
+        case PB_KIND_CAMERA: remap_direct_kernel<OUT_KIND, PB_KIND_CAMERA><<<grid, 256, 0, st>>>(a); break;
+        case PB_KIND_DOUBLE: remap_direct_kernel<OUT_KIND, PB_KIND_DOUBLE><<<grid, 256, 0, st>>>(a); break;
+        default: remap_direct_kernel<OUT_KIND, PB_KIND_EQUIRECT><<<grid, 256, 0, st>>>(a); break;
+    }
+}
+
+static void launch_direct(const RemapArgs& a, cudaStream_t st) {
+    dim3 grid((a.out.W + kTileW - 1) / kTileW, (a.out.H + kTileH - 1) / kTileH);
+    switch (a.out.kind) {
+        case PB_KIND_CAMERA: launch_direct_s<PB_KIND_CAMERA>(a, grid, st); break;
+        case PB_KIND_DOUBLE: launch_direct_s<PB_KIND_DOUBLE>(a, grid, st); break;
+        default: launch_direct_s<PB_KIND_EQUIRECT>(a, grid, st); break;
     }
 }
 
@@ -740,7 +802,29 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
     const bool tiled_ok = C == 3 && aligned16(src) && aligned16(dst) && src_pitch % 16 == 0 && dst_pitch % 16 == 0 &&
                           (!multi || (src_frame_stride % 16 == 0 && dst_frame_stride % 16 == 0)) &&
                           src_pitch * p.src.H < (1LL << 31);
-    if (tiled_ok) {
+    // one frame through a non-separable geometry: direct gathers (see remap_direct_kernel)
+    static const bool direct_off = std::getenv("PB_DIRECT") && std::atoi(std::getenv("PB_DIRECT")) == 0;  // experiments
+    const bool separable_run = p.separable && tables != nullptr;
+    if (n_frames == 1 && !separable_run && !direct_off && C == 3 && p.out.W % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(dst) & 3u) == 0 && src_pitch * p.src.H < (1LL << 31) &&
+        (p.out.H + kTileH - 1) / kTileH < 65536) {
+        RemapArgs a;
+        a.out = p.out;
+        a.src = p.src;
+        a.rot = p.rot;
+        a.fast = p.fast;
+        a.src_px = src;
+        a.dst_px = dst;
+        a.src_frame_stride = src_frame_stride;
+        a.dst_frame_stride = dst_frame_stride;
+        a.n_frames = 1;
+        launch_direct(a, st);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "direct remap launch");
+        return PB_OK;
+    }
+    static const bool tiled_off = std::getenv("PB_TILED") && std::atoi(std::getenv("PB_TILED")) == 0;  // experiments
+    if (tiled_ok && !tiled_off) {
         TiledArgs a;
         std::memset(&a, 0, sizeof(a));
         a.out = p.out;

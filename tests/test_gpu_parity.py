@@ -297,6 +297,14 @@ def test_tiled_fast_path_mid_size_batches(torch_cuda, src_kind):
     # a rotated double-fisheye source may differ by the 1-LSB blend-truncation class only
     assert n_bad == 0 or (src_kind == "double" and max_abs == 1 and n_bad / (got.shape[0] * got.shape[1]) <= 1e-4), \
         (src_kind, n_bad, max_abs)
+    # the same rotated geometry as a device batch: the tiled kernel with generic rays (resolved
+    # once per tile, applied to every frame) must give what the single-frame direct kernel gave
+    batch_out = helpers.product_image(sg, torch.from_numpy(frames[:2]).cuda()).process_coordinate_map(
+        helpers.product_map(og, rots)).cpu().numpy()
+    assert np.array_equal(batch_out[0], got), src_kind
+    _, max_abs1, n_bad1 = mismatch_report(batch_out[1], numpy_port.remap(og, rots, sg, frames[1]))
+    assert n_bad1 == 0 or (src_kind == "double" and max_abs1 == 1 and n_bad1 / (got.shape[0] * got.shape[1]) <= 1e-4), \
+        (src_kind, n_bad1, max_abs1)
 
 
 def _mid_size_geometries():
