@@ -282,8 +282,11 @@ __global__ void __launch_bounds__(256) remap_generic_kernel(const __grid_constan
 // because a warp's 32 byte-gathers of a smooth mapping touch only 8-12 sectors that mostly hit L1
 // (measured: cfg2 153 -> 142 us even with the one-pixel-per-thread generic kernel).
 // C = 3, W % 4 == 0, dst 4-byte aligned: a quad is 12 contiguous bytes = three aligned words.
+#ifndef PB_DIRECT_MIN_CTAS
+#define PB_DIRECT_MIN_CTAS 4
+#endif
 template <int OUT_KIND, int SRC_KIND>
-__global__ void __launch_bounds__(256, 3) remap_direct_kernel(const __grid_constant__ RemapArgs a) {
+__global__ void __launch_bounds__(256, PB_DIRECT_MIN_CTAS) remap_direct_kernel(const __grid_constant__ RemapArgs a) {
     constexpr bool DBL = (SRC_KIND == PB_KIND_DOUBLE);
     const int tid = threadIdx.x;
     const int j0 = blockIdx.x * kTileW + 4 * (tid & 7);
