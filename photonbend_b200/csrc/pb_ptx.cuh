@@ -164,6 +164,27 @@ __device__ __forceinline__ uint32_t lds_pixel(uint32_t word_sa, uint32_t offset,
     return __funnelshift_r(lo, hi, shift);
 }
 
+// The same with the second word loaded only by the lanes whose pixel runs into it (byte offset
+// 2 or 3 within the word): half the lanes sit the second LDS out, which roughly halves its bank
+// conflicts, at the price of one predicate-setting instruction.
+__device__ __forceinline__ uint32_t lds_pixel_pred(uint32_t byte_sa) {
+    uint32_t lo, hi;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 a, t;\n\t"
+        "and.b32 a, %2, 0xfffffffc;\n\t"
+        "and.b32 t, %2, 2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "ld.shared.b32 %0, [a];\n\t"
+        "mov.b32 %1, 0;\n\t"
+        "@p ld.shared.b32 %1, [a+4];\n\t"
+        "}"
+        : "=r"(lo), "=r"(hi)
+        : "r"(byte_sa));
+    return __funnelshift_r(lo, hi, byte_sa << 3);
+}
+
 __device__ __forceinline__ void sts32(uint32_t sa, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
 }

@@ -82,6 +82,15 @@ __global__ void __launch_bounds__(256) pb_sep1_slices_kernel(const double* __res
     }
 }
 
+// The 3 bytes of the staged pixel at byte offset off.  Single-lens source: the second word is
+// loaded only by the lanes that need it (T x1 47.0 -> 45.4 us); double source: both words always
+// (the predicate costs more than the conflicts it saves there: 74.4 vs 76.2 us).
+template <bool PRED>
+__device__ __forceinline__ unsigned sep1_pick(unsigned stage_sa, int off) {
+    if (PRED) return ptx::lds_pixel_pred(stage_sa + (unsigned)off);
+    return ptx::lds_pixel(stage_sa, (unsigned)off & ~3u, (unsigned)off << 3);
+}
+
 struct Sep1Slot {
     int nbox, pitch, rect, by0, xb0, origin, tile;
     bool all_valid;
@@ -241,7 +250,7 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
                             int px = trunc_abs(fx);
                             if (s) px = a.src.W - 1 - px;
                             const int off = trunc_abs(fy) * S.pitch + (px * 3 + base);
-                            g[q][k] = ptx::lds_pixel(stage_sa, (unsigned)off & ~3u, (unsigned)off << 3);
+                            g[q][k] = sep1_pick<!DBL>(stage_sa, off);
                         }
                 } else {
 #pragma unroll
@@ -254,7 +263,7 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
                             if (s) px = a.src.W - 1 - px;
                             int off = trunc_abs(fy) * S.pitch + (px * 3 + base);
                             off = inside_image(fx, fy, w, a.src.H) ? off : 0;  // 0: the buffer's zero bytes
-                            g[q][k] = ptx::lds_pixel(stage_sa, (unsigned)off & ~3u, (unsigned)off << 3);
+                            g[q][k] = sep1_pick<!DBL>(stage_sa, off);
                         }
                 }
             } else {
