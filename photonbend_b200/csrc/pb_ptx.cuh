@@ -185,6 +185,24 @@ __device__ __forceinline__ uint32_t lds_pixel_pred(uint32_t byte_sa) {
     return __funnelshift_r(lo, hi, byte_sa << 3);
 }
 
+// lds_pixel with the second word loaded only where the pixel runs into it (shift = 16 or 24)
+__device__ __forceinline__ uint32_t lds_pixel_sparse(uint32_t word_sa, uint32_t offset, uint32_t shift) {
+    uint32_t lo, hi;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %3, 16;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "ld.shared.b32 %0, [%2];\n\t"
+        "mov.b32 %1, 0;\n\t"
+        "@p ld.shared.b32 %1, [%2+4];\n\t"
+        "}"
+        : "=r"(lo), "=r"(hi)
+        : "r"(word_sa + offset), "r"(shift));
+    return __funnelshift_r(lo, hi, shift);
+}
+
 __device__ __forceinline__ void sts32(uint32_t sa, uint32_t v) {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
 }
