@@ -449,17 +449,26 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     if (MODE == 1) {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) fpv[s] = __ldg(a.tile_fp + (tile_y * a.tiles_x + tile_x) * NSLOT + s);
+        // per-tile slices of the tables in the layout of pb_sep1_slices_kernel: for each of its 4
+        // columns a warp reads 128 contiguous bytes (the [W][2] table read at a 64-byte stride cost
+        // ~12 L1 wavefronts per LDG.128), rows past the image edge repeat the last row
+        {
+            const double2* __restrict__ col = reinterpret_cast<const double2*>(a.sep1_col) + tile_x * kTileW;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cs[k] = __ldg(reinterpret_cast<const double2*>(a.col_tab) + min(jx + k, a.out.W - 1));
+            for (int k = 0; k < 4; ++k) cs[k] = __ldg(col + k * 8 + qc);
 #pragma unroll
-        for (int q = 0; q < kRowsPerThread; ++q) {
-            // rows past the image edge repeat the last row: they widen nothing and TMA clips them
-            const int i = min(y0 + rg + q * kRowGroups, a.out.H - 1);
-            r01[q] = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i);
-            if (DBL) {
-                const double2 r23 = __ldg(reinterpret_cast<const double2*>(a.row_tab) + 2 * i + 1);
-                wrow[q][0] = r23.x;
-                wrow[q][1] = r23.y;
+            for (int q = 0; q < kRowsPerThread; ++q) {
+                const int r = tile_y * kTileH + rg + q * kRowGroups;
+                if (DBL) {
+                    const double2* __restrict__ row = reinterpret_cast<const double2*>(a.sep1_row) + 2 * r;
+                    r01[q] = __ldg(row);
+                    const double2 r23 = __ldg(row + 1);
+                    wrow[q][0] = r23.x;
+                    wrow[q][1] = r23.y;
+                } else {
+                    r01[q].x = __ldg(a.sep1_row + r);
+                    r01[q].y = 0.0;
+                }
             }
         }
         // barrier init + zeroed tails visible; and: is every blend weight of the tile exactly 1?
