@@ -1,0 +1,7 @@
+out=gpurun_out
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "full_size or mid_size or tiny" 2>&1 | tail -2
+PB_SEP1_CHUNKED=1 timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "full_size or mid_size or tiny" 2>&1 | tail -2
+K="timeout 120 python tests/analysis/kbench.py T:1 cfg1:1 cfg4:1"
+$K --tag "interleaved"
+PB_SEP1_CHUNKED=1 $K --tag "chunked"
+PB_SEP1_CHUNKED=1 PB_SEP1_WAVES=2 $K --tag "chunked waves2"
