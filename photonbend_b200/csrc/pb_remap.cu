@@ -498,16 +498,20 @@ static bool encode_frames_map(CUtensorMap* map, const void* base, long long pitc
 }
 
 constexpr int kMaxTiledSmem = 200 * 1024;
+constexpr int kMaxDevices = 64;
 
 template <int OUT_KIND, int SRC_KIND, int MODE>
 static cudaError_t launch_tiled_one(const TiledArgs& a, cudaStream_t st) {
     const int smem = tiled_smem_bytes<SRC_KIND, MODE>(a.stage_bytes, a.n_buffers, a.n_out);
-    static bool configured = false;  // per instantiation; the attribute is per device function
-    if (!configured) {
+    // per instantiation and per device: the attribute belongs to the function on one device
+    static bool configured[kMaxDevices] = {false};
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev)) return e;
+    if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTiledSmem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
     }
     remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE><<<a.tiles_x * a.tiles_y, kTileThreads, smem, st>>>(a);
     return cudaGetLastError();
@@ -540,15 +544,16 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 template <int SRC_KIND>
 static cudaError_t launch_sep1_one(const TiledArgs& a, cudaStream_t st) {
     const int smem = sep1_smem_bytes(a.sep1_cap, SRC_KIND == PB_KIND_DOUBLE);
-    static int max_smem_set = 0;
-    if (smem > max_smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(remap_sep1_kernel<SRC_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        max_smem_set = smem;
-    }
+    static int max_smem_set[kMaxDevices] = {0};  // per device: the attribute belongs to the function on one device
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices || smem > max_smem_set[dev]) {
+        e = cudaFuncSetAttribute(remap_sep1_kernel<SRC_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < kMaxDevices) max_smem_set[dev] = smem;
+    }
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, remap_sep1_kernel<SRC_KIND>, kTileThreads, smem);
     if (e != cudaSuccess) return e;

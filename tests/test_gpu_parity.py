@@ -397,3 +397,26 @@ def test_tiny_and_degenerate_sizes(torch_cuda):
         n_unstable += int(diff.sum())
         n_px += want.shape[0] * want.shape[1]
     print(f"tiny sizes: {n_px} pixels, {n_unstable} differ on libm-dependent boundaries of the reference")
+
+
+def test_second_device_in_one_process(torch_cuda):
+    """One process driving two GPUs (FramePipeline(device=1), tensors on cuda:1): plans, function
+    attributes and tables are per device.  Skipped on a single-GPU box."""
+    torch = torch_cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle import numpy_port
+
+    sg = {"kind": "double", "height": 336, "width": 672, "lens": "equidistant", "fov": case_matrix.rad(195)}
+    og = {"kind": "equirect", "height": 352, "width": 704}
+    frames = np.stack([case_matrix.case_image(sg, 900 + k) for k in range(2)])
+    want = [numpy_port.remap(og, (), sg, f) for f in frames]
+    for dev in (0, 1, 0):
+        batch = torch.from_numpy(frames).to(f"cuda:{dev}")
+        out = helpers.product_image(sg, batch).process_coordinate_map(helpers.product_map(og, ()))
+        assert out.device.index == dev
+        single = helpers.product_image(sg, batch[1]).process_coordinate_map(helpers.product_map(og, ()))
+        rotated = helpers.product_image(sg, batch[0]).process_coordinate_map(helpers.product_map(og, [(0.3, -0.7, 1.1)]))
+        assert np.array_equal(out.cpu().numpy()[0], want[0]) and np.array_equal(out.cpu().numpy()[1], want[1]), dev
+        assert np.array_equal(single.cpu().numpy(), want[1]), dev
+        assert mismatch_report(rotated.cpu().numpy(), numpy_port.remap(og, [(0.3, -0.7, 1.1)], sg, frames[0]))[2] <= 25, dev
