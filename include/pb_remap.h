@@ -114,6 +114,16 @@ typedef struct pb_plan pb_plan;
 int pb_plan_create(const pb_remap_desc *desc, void *stream, pb_plan **plan);
 int pb_plan_remap_u8(const pb_plan *plan, const uint8_t *src, int64_t src_frame_stride, uint8_t *dst,
                      int64_t dst_frame_stride, int32_t n_frames, void *stream);
+/*
+ * Output rows [row_begin, row_end) of ONE frame: dst_band (device) holds (row_end - row_begin) x
+ * pb_output_width(out) x channels bytes, i.e. the band alone.  This is how a single large frame is
+ * sharded over the GPUs of a box by output-row bands: every GPU holds the whole source and
+ * produces its own band, no exchange (the reference's protocol works on any row slice of the
+ * coordinate map the same way: photonbend/core/projection.py:197-245 takes any (h, w, 3) map).
+ * Bands that start on a multiple of 64 rows take the TMA-staged kernels.
+ */
+int pb_plan_remap_rows_u8(const pb_plan *plan, const uint8_t *src, uint8_t *dst_band,
+                          int32_t row_begin, int32_t row_end, void *stream);
 void pb_plan_destroy(pb_plan *plan);
 
 /*

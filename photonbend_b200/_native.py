@@ -32,6 +32,7 @@ EXPORTS = (
     "pb_remap_u8",
     "pb_plan_create",
     "pb_plan_remap_u8",
+    "pb_plan_remap_rows_u8",
     "pb_plan_destroy",
     "pb_materialize_map_f64",
     "pb_rotate_map_f64",
@@ -94,6 +95,8 @@ def load():
     lib.pb_plan_create.argtypes = [ctypes.POINTER(RemapDesc), vp, ctypes.POINTER(vp)]
     lib.pb_plan_remap_u8.restype = ctypes.c_int
     lib.pb_plan_remap_u8.argtypes = [vp, vp, i64, vp, i64, i32, vp]
+    lib.pb_plan_remap_rows_u8.restype = ctypes.c_int
+    lib.pb_plan_remap_rows_u8.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.pb_plan_destroy.restype = None
     lib.pb_plan_destroy.argtypes = [vp]
     lib.pb_materialize_map_f64.restype = ctypes.c_int

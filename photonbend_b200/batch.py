@@ -9,7 +9,9 @@ make a stream cheap on a B200:
   when they are issued on separate CUDA streams from pinned memory (``FramePipeline``).
 
 Sharding over the GPUs of a box needs no collective: frame k goes to GPU k mod G
-(``shard_frames``), every GPU owns its inputs and outputs.
+(``shard_frames``), every GPU owns its inputs and outputs.  A single large frame can instead be
+cut into output-row bands (``shard_rows`` + ``remap_row_band``): every GPU holds the whole source
+and produces its band.
 """
 
 from __future__ import annotations
@@ -26,6 +28,33 @@ def shard_frames(n_frames: int, rank: int, world_size: int) -> range:
     if not 0 <= rank < world_size:
         raise ValueError(f"rank {rank} outside world of size {world_size}")
     return range(rank, n_frames, world_size)
+
+
+ROW_BAND_ALIGN = 64  # rows of one output tile: bands that start on a tile row take the TMA-staged kernels
+
+
+def shard_rows(height: int, rank: int, world_size: int, align: int = ROW_BAND_ALIGN) -> range:
+    """Output rows of rank ``rank`` when ONE frame of ``height`` rows is cut into ``world_size``
+    contiguous bands whose first rows are multiples of ``align`` (the last band takes what is
+    left; ranks beyond the number of aligned bands get an empty range).  Every GPU needs the whole
+    source; nothing is exchanged."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of size {world_size}")
+    units = -(-height // align)                       # tile rows in the image
+    lo = (units * rank) // world_size * align
+    hi = (units * (rank + 1)) // world_size * align
+    return range(min(lo, height), min(hi, height))
+
+
+def remap_row_band(source, coordinate_map: CoordinateMap, frame, rows: range, out=None):
+    """Rows ``rows`` (a contiguous range) of the remap of ONE device frame: the band alone, as a
+    (len(rows), Wo, C) CUDA tensor.  ``frame`` is the whole source image on this device."""
+    if not (isinstance(coordinate_map, CoordinateMap) and coordinate_map.is_lazy):
+        raise ValueError("remap_row_band needs the lazy CoordinateMap of get_coordinate_map()")
+    if rows.step != 1:
+        raise ValueError("a band is a contiguous range of rows")
+    return engine.remap_rows_device(coordinate_map.rays, source._source_geometry(), frame.contiguous(),
+                                    rows.start, max(rows.start, rows.stop), out)
 
 
 def max_over_ranks(values, device="cpu"):

@@ -228,6 +228,7 @@ struct RemapArgs {
     unsigned char* dst_px;
     long long src_frame_stride, dst_frame_stride;
     int n_frames;
+    int row_begin, row_end;  // output rows this launch covers; dst_px points at row row_begin
 };
 
 template <int C>
@@ -247,14 +248,14 @@ __device__ __forceinline__ void zero_px(unsigned char* __restrict__ d) {
 template <int OUT_KIND, int SRC_KIND, int C>
 __global__ void __launch_bounds__(256) remap_generic_kernel(const __grid_constant__ RemapArgs a) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= a.out.H || j >= a.out.W) return;
+    const int i = a.row_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= a.row_end || j >= a.out.W) return;
 
     const Lookup L = resolve_lookup<OUT_KIND, SRC_KIND>(a.out, a.fast, a.rot, a.src, i, j);
     const int off0 = xy_to_offset(L.xy0, a.src.W);
     const int off1 = xy_to_offset(L.xy1, a.src.W);
 
-    const long long dst_off = ((long long)i * a.out.W + j) * C;
+    const long long dst_off = ((long long)(i - a.row_begin) * a.out.W + j) * C;
     for (int f = 0; f < a.n_frames; ++f) {
         const unsigned char* __restrict__ sp = a.src_px + f * a.src_frame_stride;
         unsigned char* __restrict__ dp = a.dst_px + f * a.dst_frame_stride + dst_off;
@@ -295,8 +296,8 @@ __global__ void __launch_bounds__(256, PB_DIRECT_MIN_CTAS) remap_direct_kernel(c
     const int src_pitch = a.src.W * 3;
 #pragma unroll 1
     for (int q = 0; q < 2; ++q) {
-        const int i = blockIdx.y * kTileH + (tid >> 3) + q * 32;
-        if (i >= a.out.H) break;
+        const int i = a.row_begin + blockIdx.y * kTileH + (tid >> 3) + q * 32;
+        if (i >= a.row_end) break;
         unsigned long long lo = 0;  // bytes 0..7 of the quad
         unsigned hi = 0;            // bytes 8..11
 #pragma unroll 1
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(256, PB_DIRECT_MIN_CTAS) remap_direct_kernel(c
             if (k == 2) hi |= px >> 16;
             if (k == 3) hi |= px << 8;
         }
-        unsigned* o = reinterpret_cast<unsigned*>(a.dst_px + ((long long)i * a.out.W + j0) * 3);
+        unsigned* o = reinterpret_cast<unsigned*>(a.dst_px + ((long long)(i - a.row_begin) * a.out.W + j0) * 3);
         o[0] = (unsigned)lo;
         o[1] = (unsigned)(lo >> 32);
         o[2] = hi;
@@ -402,7 +403,7 @@ __global__ void __launch_bounds__(256) gather_from_map_kernel(const __grid_const
 template <int OUT_KIND, int SRC_KIND>
 static void launch_generic_c(const RemapArgs& a, cudaStream_t st) {
     dim3 block(32, 8);
-    dim3 grid((a.out.W + block.x - 1) / block.x, (a.out.H + block.y - 1) / block.y);
+    dim3 grid((a.out.W + block.x - 1) / block.x, (a.row_end - a.row_begin + block.y - 1) / block.y);
     switch (a.src.C) {
         case 1: remap_generic_kernel<OUT_KIND, SRC_KIND, 1><<<grid, block, 0, st>>>(a); break;
         case 2: remap_generic_kernel<OUT_KIND, SRC_KIND, 2><<<grid, block, 0, st>>>(a); break;
@@ -430,7 +431,7 @@ static void launch_direct_s(const RemapArgs& a, dim3 grid, cudaStream_t st) {
 }
 
 static void launch_direct(const RemapArgs& a, cudaStream_t st) {
-    dim3 grid((a.out.W + kTileW - 1) / kTileW, (a.out.H + kTileH - 1) / kTileH);
+    dim3 grid((a.out.W + kTileW - 1) / kTileW, (a.row_end - a.row_begin + kTileH - 1) / kTileH);
     switch (a.out.kind) {
         case PB_KIND_CAMERA: launch_direct_s<PB_KIND_CAMERA>(a, grid, st); break;
         case PB_KIND_DOUBLE: launch_direct_s<PB_KIND_DOUBLE>(a, grid, st); break;
@@ -802,8 +803,13 @@ static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st
 }
 
 // tables: the plan's own, a transient stream-ordered allocation, or null (generic rays)
+// [row_begin, row_end): the output rows to produce; dst points at row row_begin (a band of a
+// single frame, or the whole image)
 static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, int64_t src_frame_stride,
-                    uint8_t* dst, int64_t dst_frame_stride, int32_t n_frames, cudaStream_t st) {
+                    uint8_t* dst, int64_t dst_frame_stride, int32_t n_frames, cudaStream_t st, int row_begin = 0,
+                    int row_end = -1) {
+    if (row_end < 0) row_end = p.out.H;
+    const bool whole = row_begin == 0 && row_end == p.out.H;
     const int C = p.desc.channels;
     const long long src_pitch = (long long)p.src.W * C, dst_pitch = (long long)p.out.W * C;
     const bool multi = n_frames > 1;
@@ -812,7 +818,8 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
                           src_pitch * p.src.H < (1LL << 31);
     // one frame through a non-separable geometry: direct gathers (see remap_direct_kernel)
     static const bool direct_off = std::getenv("PB_DIRECT") && std::atoi(std::getenv("PB_DIRECT")) == 0;  // experiments
-    const bool separable_run = p.separable && tables != nullptr;
+    // (a separable geometry takes the tiled kernels when the band starts on a tile row)
+    const bool separable_run = p.separable && tables != nullptr && row_begin % kTileH == 0;
     if (n_frames == 1 && !separable_run && !direct_off && C == 3 && p.out.W % 4 == 0 &&
         (reinterpret_cast<uintptr_t>(dst) & 3u) == 0 && src_pitch * p.src.H < (1LL << 31) &&
         (p.out.H + kTileH - 1) / kTileH < 65536) {
@@ -826,13 +833,15 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         a.src_frame_stride = src_frame_stride;
         a.dst_frame_stride = dst_frame_stride;
         a.n_frames = 1;
+        a.row_begin = row_begin;
+        a.row_end = row_end;
         launch_direct(a, st);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "direct remap launch");
         return PB_OK;
     }
     static const bool tiled_off = std::getenv("PB_TILED") && std::atoi(std::getenv("PB_TILED")) == 0;  // experiments
-    if (tiled_ok && !tiled_off) {
+    if (tiled_ok && !tiled_off && row_begin % kTileH == 0) {
         TiledArgs a;
         std::memset(&a, 0, sizeof(a));
         a.out = p.out;
@@ -851,7 +860,8 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
         a.n_frames = n_frames;
         a.src_pitch = (int)src_pitch;
         a.tiles_x = tiles_x(p);
-        a.tiles_y = tiles_y(p);
+        a.tile_y0 = row_begin / kTileH;
+        a.tiles_y = (row_end - row_begin + kTileH - 1) / kTileH;
         a.raster_band = p.raster_band;
         // L2 prefetch (UTMAPF) of frames beyond those in flight: worth +7 % on a single-lens source
         // while tiles kept two frames in flight; with the ring of frame groups it is neutral
@@ -887,12 +897,12 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
             maps_ok = encode_frames_map(&a.src_maps[(u - kMinStageUnits) / 2], src, src_pitch, p.src.H, n_frames,
                                         src_frame_stride, 2, 16 * u, kBoxRows);
         if (maps_ok &&
-            encode_frames_map(&a.dst_map, dst, dst_pitch, p.out.H, n_frames, dst_frame_stride, 1, kOutRowBytes,
-                              kTileH)) {
+            encode_frames_map(&a.dst_map, dst, dst_pitch, row_end - row_begin, n_frames, dst_frame_stride, 1,
+                              kOutRowBytes, kTileH)) {
             const bool sep = p.separable && tables != nullptr;
             static const bool sep1_off = std::getenv("PB_SEP1") && std::atoi(std::getenv("PB_SEP1")) == 0;
             cudaError_t e;
-            if (sep && n_frames == 1 && !sep1_off && p.out.W / kTileW < 65536 && p.out.H / kTileH < 32768)
+            if (sep && whole && n_frames == 1 && !sep1_off && p.out.W / kTileW < 65536 && p.out.H / kTileH < 32768)
                 e = a.src.kind == PB_KIND_CAMERA ? launch_sep1_one<PB_KIND_CAMERA>(a, st)
                                                  : launch_sep1_one<PB_KIND_DOUBLE>(a, st);
             else
@@ -912,6 +922,8 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
     a.src_frame_stride = src_frame_stride;
     a.dst_frame_stride = dst_frame_stride;
     a.n_frames = n_frames;
+    a.row_begin = row_begin;
+    a.row_end = row_end;
     launch_generic(a, st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "generic remap launch");
@@ -995,6 +1007,18 @@ int pb_plan_remap_u8(const pb_plan* plan, const uint8_t* src, int64_t src_frame_
     if (cudaGetDevice(&dev) != cudaSuccess || dev != plan->device)
         return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_remap_u8: plan belongs to another device");
     return plan_run(*plan, plan->tables, src, src_frame_stride, dst, dst_frame_stride, n_frames, (cudaStream_t)stream);
+}
+
+int pb_plan_remap_rows_u8(const pb_plan* plan, const uint8_t* src, uint8_t* dst_band, int32_t row_begin, int32_t row_end,
+                          void* stream) {
+    if (!plan || !src || !dst_band) return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_remap_rows_u8: null pointer");
+    if (row_begin < 0 || row_end > plan->out.H || row_begin > row_end)
+        return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_remap_rows_u8: rows outside the output image");
+    if (row_begin == row_end) return PB_OK;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != plan->device)
+        return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_remap_rows_u8: plan belongs to another device");
+    return plan_run(*plan, plan->tables, src, 0, dst_band, 0, 1, (cudaStream_t)stream, row_begin, row_end);
 }
 
 void pb_plan_destroy(pb_plan* plan) {

@@ -77,7 +77,9 @@ struct TiledArgs {
     int n_buffers;    // stage buffers: 1, or 2 (loads of the next item overlap the current gather)
     int n_out;        // output tile buffers: 1, or 2 (the store of frame f overlaps frame f+1)
     int* probe;       // non-null: footprint census only (see pb_plan_create), nothing is remapped
-    int tiles_x, tiles_y;  // tiles per output row / column
+    int tiles_x, tiles_y;  // tiles per output row / column (of the row band this launch covers)
+    int tile_y0;           // first tile row of the band; the band's first output row is tile_y0 * 64
+                           // and dst_map describes the band alone (pb_plan_remap_rows_u8)
     int lean_min_groups;  // tiles that cannot keep this many frames in flight use the (frame, slot) item loop
     int l2_ahead;     // items whose boxes are prefetched into L2 ahead of the shared-memory loads
     int raster_band;  // CTAs walk bands of this many tile rows column by column (0: plain row-major)
@@ -371,7 +373,7 @@ __device__ __noinline__ void direct_tile(const TiledArgs& a, const int* xy_scrat
         ptx::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
-            ptx::tma_store_3d(&a.dst_map, x0 * 3, y0, f, out_tile);
+            ptx::tma_store_3d(&a.dst_map, x0 * 3, y0 - a.tile_y0 * kTileH, f, out_tile);
             ptx::bulk_commit();
         }
     }
@@ -418,8 +420,10 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         tile_y = blockIdx.x / a.tiles_x;
         tile_x = blockIdx.x - tile_y * a.tiles_x;
     }
+    tile_y += a.tile_y0;
     const int x0 = tile_x * kTileW;
     const int y0 = tile_y * kTileH;
+    const int ys = y0 - a.tile_y0 * kTileH;  // row of the tile in the destination this launch writes
     const int jx = x0 + 4 * qc;
 
     if (tid == 0) {
@@ -735,7 +739,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                 __syncthreads();
                 if (tid == 0) {
                     if (f + n_groups < a.n_frames) issue_group(f + n_groups, g);
-                    ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, y0, f, out_tiles + (f & 1) * out_flip, drop);
+                    ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, ys, f, out_tiles + (f & 1) * out_flip, drop);
                     ptx::bulk_commit();
                     if (a.l2_ahead > 0 && f + n_groups + a.l2_ahead < a.n_frames) prefetch_group(f + n_groups + a.l2_ahead);
                 }
@@ -830,7 +834,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         ptx::fence_async_smem();
         __syncthreads();
         if (tid == 0 && !dbg_nostore) {
-            ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, y0, f, out_tile, ptx::policy_evict_first());
+            ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, ys, f, out_tile, ptx::policy_evict_first());
             ptx::bulk_commit();
         }
     }

@@ -221,6 +221,35 @@ def remap_device(rays: RayPlan, src: ImageGeometry, src_dev, out_dev=None):
     return out_dev
 
 
+def remap_rows_device(rays: RayPlan, src: ImageGeometry, src_dev, row_begin: int, row_end: int, out_dev=None):
+    """Output rows [row_begin, row_end) of one frame (pb_plan_remap_rows_u8): src_dev is the WHOLE
+    source image on this device, the result is the band alone, (row_end - row_begin, Wo[, C])."""
+    torch = _torch()
+    lib = _native.load()
+    if src_dev.dim() == 4:
+        raise ValueError("a row band is cut from ONE frame, not from a batch")
+    h, w, c, had_c = image_layout(src_dev)
+    if (h, w) != (src.height, src.width):
+        raise ValueError(f"source image is {h}x{w} but its geometry says {src.height}x{src.width}")
+    oh, ow = rays.out.height, rays.out.output_width
+    if not 0 <= row_begin <= row_end <= oh:
+        raise ValueError(f"rows [{row_begin}, {row_end}) outside an output of {oh} rows")
+    out_shape = (row_end - row_begin, ow, c) if had_c else (row_end - row_begin, ow)
+    if out_dev is None:
+        out_dev = torch.empty(out_shape, dtype=torch.uint8, device=src_dev.device)
+    elif tuple(out_dev.shape) != out_shape or not out_dev.is_contiguous() or out_dev.dtype != torch.uint8:
+        raise ValueError(f"out must be a contiguous uint8 tensor of shape {out_shape}")
+    if row_begin == row_end:
+        return out_dev
+    desc = _remap_desc(rays, src, c)
+    with torch.cuda.device(src_dev.device):
+        plan = _plans.get(lib, desc, src_dev.device.index or 0, torch)
+        _native.check(lib.pb_plan_remap_rows_u8(
+            plan, ctypes.c_void_p(src_dev.data_ptr()), ctypes.c_void_p(out_dev.data_ptr()),
+            ctypes.c_int32(row_begin), ctypes.c_int32(row_end), _stream_ptr(torch)))
+    return out_dev
+
+
 def materialize_map_device(rays: RayPlan):
     """float64 CUDA tensor (H, W, 3) of the coordinate map described by ``rays``."""
     torch = _torch()

@@ -420,3 +420,25 @@ def test_second_device_in_one_process(torch_cuda):
         assert np.array_equal(out.cpu().numpy()[0], want[0]) and np.array_equal(out.cpu().numpy()[1], want[1]), dev
         assert np.array_equal(single.cpu().numpy(), want[1]), dev
         assert mismatch_report(rotated.cpu().numpy(), numpy_port.remap(og, [(0.3, -0.7, 1.1)], sg, frames[0]))[2] <= 25, dev
+
+
+@pytest.mark.parametrize("rots", [(), ((0.3, -0.7, 1.1),)], ids=["separable", "rotated"])
+def test_row_bands_equal_the_whole_frame(torch_cuda, rots):
+    """pb_plan_remap_rows_u8 / batch.remap_row_band: a frame cut into output-row bands (tile-aligned
+    ones from shard_rows, and odd ones) gives exactly the rows of the whole-frame remap."""
+    torch = torch_cuda
+    from photonbend_b200.batch import remap_row_band, shard_rows
+
+    sg = {"kind": "double", "height": 336, "width": 672, "lens": "equidistant", "fov": case_matrix.rad(195)}
+    og = {"kind": "equirect", "height": 420, "width": 704}
+    frame = torch.from_numpy(case_matrix.case_image(sg, 77)).cuda()
+    source = helpers.product_image(sg, frame)
+    cmap = helpers.product_map(og, rots)
+    whole = source.process_coordinate_map(cmap).cpu().numpy()
+    for world in (1, 2, 3, 8):
+        bands = [remap_row_band(source, cmap, frame, shard_rows(og["height"], r, world)) for r in range(world)]
+        got = torch.cat(bands, dim=0).cpu().numpy()
+        assert np.array_equal(got, whole), (rots, world)
+    for rows in (range(0, 1), range(5, 133), range(64, 65), range(419, 420), range(100, 100)):
+        band = remap_row_band(source, cmap, frame, rows).cpu().numpy()
+        assert np.array_equal(band, whole[rows.start:rows.stop]), (rots, rows)

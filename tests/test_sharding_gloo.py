@@ -65,3 +65,51 @@ def test_two_gloo_ranks_cover_the_stream(tmp_path):
     assert sorted(got) == list(range(n_frames))
     for k in range(n_frames):
         assert np.array_equal(got[k], numpy_port.remap(og, (), sg, case_matrix.case_image(sg, 500 + k)))
+
+
+def test_shard_rows_partitions_every_frame():
+    """Row bands of one frame: disjoint, contiguous, cover [0, H), start on tile rows."""
+    from photonbend_b200.batch import ROW_BAND_ALIGN, shard_rows
+
+    for h in (1, 63, 64, 65, 1000, 3840, 4320):
+        for world in (1, 2, 3, 4, 8):
+            bands = [shard_rows(h, r, world) for r in range(world)]
+            rows = [i for b in bands for i in b]
+            assert rows == list(range(h)), (h, world)
+            assert all(b.start % ROW_BAND_ALIGN == 0 for b in bands if len(b))
+    bands = [len(shard_rows(3840, r, 8)) for r in range(8)]
+    assert max(bands) - min(bands) <= ROW_BAND_ALIGN
+
+
+def _band_rank_main(rank, world, port, result_dir):
+    import torch.distributed as dist
+
+    import case_matrix
+    from oracle import numpy_port
+    from photonbend_b200.batch import shard_rows
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sg = {"kind": "camera", "height": 40, "width": 40, "lens": "equidistant", "fov": case_matrix.rad(360), "magnitude": 19.5}
+    og = {"kind": "equirect", "height": 150, "width": 64}
+    image = case_matrix.case_image(sg, 321)  # every rank holds the whole source
+    band = shard_rows(og["height"], rank, world)
+    out = numpy_port.remap(og, [(0.2, 0.1, -0.3)], sg, image, rows=(band.start, band.stop))
+    np.save(os.path.join(result_dir, f"band{rank}.npy"), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_cover_one_frame_by_row_bands(tmp_path):
+    """The other way to shard (north_star: "frames or output-row bands"): two ranks, one frame."""
+    import case_matrix
+    from oracle import numpy_port
+
+    world = 2
+    mp.spawn(_band_rank_main, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    sg = {"kind": "camera", "height": 40, "width": 40, "lens": "equidistant", "fov": case_matrix.rad(360), "magnitude": 19.5}
+    og = {"kind": "equirect", "height": 150, "width": 64}
+    whole = numpy_port.remap(og, [(0.2, 0.1, -0.3)], sg, case_matrix.case_image(sg, 321))
+    got = np.concatenate([np.load(os.path.join(tmp_path, f"band{r}.npy")) for r in range(world)], axis=0)
+    assert np.array_equal(got, whole)
