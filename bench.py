@@ -446,7 +446,7 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64 index math, u8 pixels",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "dtype_note": "float64 index arithmetic on uint8 pixels",
             "data": "synthetic uniform-noise uint8 frames (seeded), generated on device",
             "config": bench_config(name, frames),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -499,7 +499,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": tot_dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64 index math, u8 pixels", "data": "synthetic uniform-noise uint8 frame (seeded)",
+        "vs_baseline": None, "dtype": "f64", "dtype_note": "float64 index arithmetic on uint8 pixels",
+        "data": "synthetic uniform-noise uint8 frame (seeded)",
         "config": bench_config(name, args.frames),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
