@@ -180,7 +180,8 @@ __device__ __forceinline__ int fast_out_vector(const OutGeom& g, const FastGeom&
             if (!(r2 > 0.0)) return 2;
             const double inv_r = rsqrt(r2);
             const double d = r2 * inv_r * inv_f;
-            const double lat = (g.lens == PB_LENS_EQUIDISTANT) ? d : asin(d / 1.47) / 0.713;
+            double lat = d;
+            if (g.lens != PB_LENS_EQUIDISTANT) lat = asin(d / 1.47) / 0.713;  // (a branch: `?:` would evaluate asin for both)
             double sl, cl;
             sincos(lat, &sl, &cl);
             k = sl * inv_r;
@@ -251,7 +252,8 @@ __device__ __forceinline__ bool fast_src_lookup(const SrcGeom& s, const FastGeom
     }
     const double inv_h = rsqrt(h2);
     if (SRC_KIND == PB_KIND_CAMERA) {
-        const double theta = lens_needs_angle(s.lens) ? fast_acos_sc(h2 * inv_h, ny) : 0.0;
+        double theta = 0.0;
+        if (lens_needs_angle(s.lens)) theta = fast_acos_sc(h2 * inv_h, ny);  // (a branch: `?:` would evaluate both)
         double q;
         const int st = fast_lens_q(s.lens, fg, ny, inv_h, theta, q);
         if (st == 2) return false;
@@ -261,7 +263,8 @@ __device__ __forceinline__ bool fast_src_lookup(const SrcGeom& s, const FastGeom
     // double source (projection.py:408-462): unit weights only, the blend band takes the exact chain
     if (!((ny > fg.ny_band_hi) || (ny < fg.ny_band_lo))) return false;
     const bool ang = lens_needs_angle(s.lens);
-    const double theta = ang ? fast_acos_sc(h2 * inv_h, ny) : 0.0;
+    double theta = 0.0;
+    if (ang) theta = fast_acos_sc(h2 * inv_h, ny);
     double ql, qr;
     const int sl = fast_lens_q(s.lens, fg, ny, inv_h, theta, ql);
     const int sr = fast_lens_q(s.lens, fg, -ny, inv_h, ang ? kPi - theta : 0.0, qr);
