@@ -106,8 +106,11 @@ struct Sep1Slot {
     }
 };
 
+#ifndef PB_SEP1_CAM_CTAS
+#define PB_SEP1_CAM_CTAS 4  // 60 registers, no spills: T x1 43.2 us (5 CTAs at 48 registers spill: 45.4 us)
+#endif
 template <int SRC_KIND>
-__global__ void __launch_bounds__(kTileThreads, (SRC_KIND == PB_KIND_DOUBLE) ? 3 : 5)
+__global__ void __launch_bounds__(kTileThreads, (SRC_KIND == PB_KIND_DOUBLE) ? 3 : PB_SEP1_CAM_CTAS)
 remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
     constexpr bool DBL = (SRC_KIND == PB_KIND_DOUBLE);
     constexpr int NSLOT = DBL ? 2 : 1;
