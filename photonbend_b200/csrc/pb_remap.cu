@@ -542,21 +542,21 @@ static cudaError_t launch_tiled(const TiledArgs& a, bool separable, cudaStream_t
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // persistent single-frame kernel: as many CTAs as the device holds at once
-template <int SRC_KIND>
+template <int SRC_KIND, int NB>
 static cudaError_t launch_sep1_one(const TiledArgs& a, cudaStream_t st) {
-    const int smem = sep1_smem_bytes(a.sep1_cap, SRC_KIND == PB_KIND_DOUBLE);
+    const int smem = sep1_smem_bytes(a.sep1_cap, SRC_KIND == PB_KIND_DOUBLE, NB);
     static int max_smem_set[kMaxDevices] = {0};  // per device: the attribute belongs to the function on one device
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= kMaxDevices || smem > max_smem_set[dev]) {
-        e = cudaFuncSetAttribute(remap_sep1_kernel<SRC_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(remap_sep1_kernel<SRC_KIND, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < kMaxDevices) max_smem_set[dev] = smem;
     }
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, remap_sep1_kernel<SRC_KIND>, kTileThreads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, remap_sep1_kernel<SRC_KIND, NB>, kTileThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     int grid = sms * per_sm;
@@ -565,7 +565,7 @@ static cudaError_t launch_sep1_one(const TiledArgs& a, cudaStream_t st) {
     const int n_tiles = a.tiles_x * a.tiles_y;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
-    remap_sep1_kernel<SRC_KIND><<<grid, kTileThreads, smem, st>>>(a);
+    remap_sep1_kernel<SRC_KIND, NB><<<grid, kTileThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -903,8 +903,17 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
             static const bool sep1_off = std::getenv("PB_SEP1") && std::atoi(std::getenv("PB_SEP1")) == 0;
             cudaError_t e;
             if (sep && whole && n_frames == 1 && !sep1_off && p.out.W / kTileW < 65536 && p.out.H / kTileH < 32768)
-                e = a.src.kind == PB_KIND_CAMERA ? launch_sep1_one<PB_KIND_CAMERA>(a, st)
-                                                 : launch_sep1_one<PB_KIND_DOUBLE>(a, st);
+            {
+                // two stage buffers; a third one (deeper prefetch) measured no faster on a single-lens
+                // source (T x1 41.5 us either way) and does not always fit: PB_SEP1_BUFFERS=3 for experiments
+                static const int nb_env = std::getenv("PB_SEP1_BUFFERS") ? std::atoi(std::getenv("PB_SEP1_BUFFERS")) : 0;
+                if (a.src.kind == PB_KIND_CAMERA)
+                    e = (nb_env == 3 && sep1_smem_bytes(a.sep1_cap, false, 3) <= kMaxTiledSmem)
+                            ? launch_sep1_one<PB_KIND_CAMERA, 3>(a, st)
+                            : launch_sep1_one<PB_KIND_CAMERA, 2>(a, st);
+                else
+                    e = launch_sep1_one<PB_KIND_DOUBLE, 2>(a, st);
+            }
             else
                 e = launch_tiled(a, sep, st);
             if (e != cudaSuccess) return cuda_fail(e, "tiled remap launch");

@@ -109,14 +109,17 @@ struct Sep1Slot {
 #ifndef PB_SEP1_CAM_CTAS
 #define PB_SEP1_CAM_CTAS 4  // 60 registers, no spills: T x1 43.2 us (5 CTAs at 48 registers spill: 45.4 us)
 #endif
-template <int SRC_KIND>
+// NB: stage buffers = depth of the load pipeline (tile n is gathered while the loads of tiles
+// n+1 .. n+NB-1 are in flight and those of tile n+NB are issued)
+template <int SRC_KIND, int NB>
 __global__ void __launch_bounds__(kTileThreads, (SRC_KIND == PB_KIND_DOUBLE) ? 3 : PB_SEP1_CAM_CTAS)
 remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
+    static_assert(NB >= 2 && NB <= 4, "2..4 stage buffers");
     constexpr bool DBL = (SRC_KIND == PB_KIND_DOUBLE);
     constexpr int NSLOT = DBL ? 2 : 1;
 
     extern __shared__ __align__(128) unsigned char smem[];
-    // [ out tile 0 ][ out tile 1 ][ stage 0 ][ stage 1 ][ ring of 4 tile descriptors ][ 2 mbarriers ]
+    // [ out tile 0 ][ out tile 1 ][ NB stage buffers ][ ring of 8 tile descriptors ][ NB mbarriers ]
     // stage buffer: [128 zero bytes][column slice 512][row slice 512 | 2048][source rectangles, up to cap bytes]
     constexpr int kColBytes = kTileW * 16;
     constexpr int kRowBytes = kTileH * (DBL ? 32 : 8);
@@ -125,8 +128,8 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
     const int buf_bytes = kHead + cap;
     unsigned char* out_tiles = smem;
     unsigned char* stages = smem + 2 * kOutTileBytes;
-    int4* ring = reinterpret_cast<int4*>(stages + 2 * buf_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 8);
+    int4* ring = reinterpret_cast<int4*>(stages + NB * buf_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 16);
 
     const int tid = threadIdx.x;
     const int qc = tid & (kQuadsPerRow - 1);
@@ -137,12 +140,12 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
 
     if (tid == 0) {
         ptx::prefetch_tensormap(&a.dst_map);
-        ptx::mbarrier_init(&bars[0], 1);
-        ptx::mbarrier_init(&bars[1], 1);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) ptx::mbarrier_init(&bars[b], 1);
         ptx::fence_mbarrier_init();
     }
-    if (tid < 16) reinterpret_cast<int4*>(stages + (tid >> 3) * buf_bytes)[tid & 7] = make_int4(0, 0, 0, 0);
-    if (tid < 3 * NSLOT) {  // descriptors of this CTA's first three tiles
+    if (tid < 8 * NB) reinterpret_cast<int4*>(stages + (tid >> 3) * buf_bytes)[tid & 7] = make_int4(0, 0, 0, 0);
+    if (tid < (NB + 1) * NSLOT) {  // descriptors of this CTA's first NB + 1 tiles
         const int k = tid / NSLOT, s = tid - k * NSLOT;
         const int u = blockIdx.x + k * G;
         ring[k * 2 + s] = (u < n_tiles) ? __ldg(tab + u * NSLOT + s) : make_int4(0, 0, 0, 0);
@@ -177,8 +180,9 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
         }
     };
     if (tid == 0) {
-        issue(0, 0);
-        if (blockIdx.x + G < n_tiles) issue(1, 1);
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+            if ((int)blockIdx.x + b * G < n_tiles) issue(b, b);
     }
 
     const uint64_t drop = ptx::policy_evict_first();
@@ -187,14 +191,14 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
     const double cy = a.src.cy;
     unsigned phase = 0;  // bit b: parity the next wait on stage buffer b expects
 
-    int it = 0;
-    for (int u = blockIdx.x; u < n_tiles; u += G, ++it) {
-        const int b = it & 1;
-        const int4 d0 = ring[(it & 3) * 2];
-        const int4 d1 = DBL ? ring[(it & 3) * 2 + 1] : make_int4(0, 0, 0, 0);
-        // the descriptor of the tile three ahead travels while this tile is processed
+    int it = 0, b = 0;
+    for (int u = blockIdx.x; u < n_tiles; u += G, ++it, b = (b + 1 == NB) ? 0 : b + 1) {
+        const int ob = it & 1;  // output tile
+        const int4 d0 = ring[(it & 7) * 2];
+        const int4 d1 = DBL ? ring[(it & 7) * 2 + 1] : make_int4(0, 0, 0, 0);
+        // the descriptor of the tile NB + 1 ahead travels while this tile is processed
         int4 pre = make_int4(0, 0, 0, 0);
-        if (tid < NSLOT && u + 3 * G < n_tiles) pre = __ldg(tab + (u + 3 * G) * NSLOT + tid);
+        if (tid < NSLOT && u + (NB + 1) * G < n_tiles) pre = __ldg(tab + (u + (NB + 1) * G) * NSLOT + tid);
 
         Sep1Slot sl[2];
         sl[0].decode(d0);
@@ -302,11 +306,11 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
             }
         }
 
-        const unsigned o = out_sa + b * kOutTileBytes;
+        const unsigned o = out_sa + ob * kOutTileBytes;
 #pragma unroll
         for (int q = 0; q < kRowsPerThread; ++q) store_quad_sa(o + q * kRowGroups * kOutRowBytes, v[q]);
         ptx::fence_async_smem();
-        if (tid < NSLOT) ring[((it + 3) & 3) * 2 + tid] = pre;
+        if (tid < NSLOT) ring[((it + NB + 1) & 7) * 2 + tid] = pre;
         // The loads of tile it + 2 and the store of this tile are issued by lane 0 of warp (it mod 8):
         // rotating the duty spreads its cost over the warps instead of making one warp late at
         // every barrier.  Bulk async-groups belong to the issuing thread, so the thread that
@@ -314,17 +318,17 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
         if (tid == (((it - 1) & 7) << 5) && it > 0) ptx::bulk_wait_read0();
         __syncthreads();
         if (tid == ((it & 7) << 5)) {
-            if (u + 2 * G < n_tiles) issue((it + 2) & 3, b);
-            ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, y0, 0, out_tiles + b * kOutTileBytes, drop);
+            if (u + NB * G < n_tiles) issue((it + NB) & 7, b);
+            ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, y0, 0, out_tiles + ob * kOutTileBytes, drop);
             ptx::bulk_commit();
         }
     }
     if ((tid & 31) == 0) ptx::bulk_wait_read0();  // every issuing thread: its stores have left shared memory
 }
 
-inline int sep1_smem_bytes(int cap, bool dbl) {
+inline int sep1_smem_bytes(int cap, bool dbl, int n_buffers) {
     const int head = 128 + kTileW * 16 + kTileH * (dbl ? 32 : 8);
-    return 2 * kOutTileBytes + 2 * (head + cap) + 8 * (int)sizeof(int4) + 16 + 128;
+    return 2 * kOutTileBytes + n_buffers * (head + cap) + 16 * (int)sizeof(int4) + 8 * n_buffers + 128;
 }
 
 }  // namespace pb
