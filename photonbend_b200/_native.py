@@ -77,11 +77,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("PB_REMAP_LIB") or LIB_PATH  # override: A/B runs of experiment builds
+    if path == LIB_PATH and not os.path.exists(LIB_PATH):
         from . import build as _build  # raises if nvcc is unavailable or compilation fails
 
         _build.build()
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
     lib.pb_version.restype = ctypes.c_int
     lib.pb_version.argtypes = []

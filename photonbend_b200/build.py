@@ -49,12 +49,13 @@ def is_stale() -> bool:
     return any(os.path.getmtime(p) > built for p in SOURCES + HEADERS + [os.path.abspath(__file__)])
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: str = LIB_PATH) -> str:
+    """out != LIB_PATH: an experiment build next to the product library (loaded with PB_REMAP_LIB)."""
+    if out == LIB_PATH and not force and not is_stale():
         return LIB_PATH
     extra = os.environ.get("PB_NVCC_EXTRA", "").split()  # e.g. -DPB_EXPERIMENTS for timing experiments
     cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(REPO, "include"), "-I", CSRC,
-           "-o", LIB_PATH, *SOURCES]
+           "-o", out, *SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
@@ -63,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return out
 
 
 def io_is_stale() -> bool:
@@ -90,4 +91,5 @@ def build_io(force: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build_io(force="--force" in sys.argv))
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    out = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")), LIB_PATH)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=out))

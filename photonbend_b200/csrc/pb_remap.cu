@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "pb_device.cuh"
 #include "pb_tiled.cuh"
@@ -501,7 +502,7 @@ static bool encode_frames_map(CUtensorMap* map, const void* base, long long pitc
 constexpr int kMaxTiledSmem = 200 * 1024;
 constexpr int kMaxDevices = 64;
 
-template <int OUT_KIND, int SRC_KIND, int MODE>
+template <int OUT_KIND, int SRC_KIND, int MODE, int CLS = 0>
 static cudaError_t launch_tiled_one(const TiledArgs& a, cudaStream_t st) {
     const int smem = tiled_smem_bytes<SRC_KIND, MODE>(a.stage_bytes, a.n_buffers, a.n_out);
     // per instantiation and per device: the attribute belongs to the function on one device
@@ -509,12 +510,14 @@ static cudaError_t launch_tiled_one(const TiledArgs& a, cudaStream_t st) {
     int dev = 0;
     if (cudaError_t e = cudaGetDevice(&dev)) return e;
     if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE>,
+        cudaError_t e = cudaFuncSetAttribute(remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE, CLS>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTiledSmem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
     }
-    remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE><<<a.tiles_x * a.tiles_y, kTileThreads, smem, st>>>(a);
+    const int grid = a.tile_list ? a.n_list : a.tiles_x * a.tiles_y;
+    if (grid <= 0) return cudaSuccess;
+    remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE, CLS><<<grid, kTileThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -538,6 +541,13 @@ static cudaError_t launch_tiled(const TiledArgs& a, bool separable, cudaStream_t
         default: return launch_tiled_generic_s<PB_KIND_EQUIRECT>(a, st);
     }
 }
+
+// tuning experiments
+static int env_int(const char* name, int fallback) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : fallback;
+}
+static bool class_split_off() { return env_int("PB_CLASS_SPLIT", 1) == 0; }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -585,6 +595,11 @@ struct pb_plan {
     int raster_band;     // tile rows per raster band (see remap_tiled_kernel)
     int sep1_cap;        // single-frame separable kernel: bytes per stage buffer
     double* tables;      // device: col_tab [W][2], row_tab [H][4], then the per-tile footprints; null unless separable
+    // separable double-fisheye source: the tiles sorted into two classes, each in raster order --
+    // [0, n_one): exactly one lens visible at unit weights, [n_one, n_one + n_rest): the rest
+    // (both lenses, blend band, nothing visible); batches run them as two launches (remap_tiled_kernel CLS)
+    int* tile_lists;
+    int n_one, n_rest;
     int device;
 };
 
@@ -619,6 +634,8 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     p.sep1_cap = (d.src.kind == PB_KIND_DOUBLE ? 48 : 24) * 1024;  // un-tuned default
     if (const char* e = std::getenv("PB_RASTER_BAND")) p.raster_band = std::atoi(e);  // tuning experiments
     p.tables = nullptr;
+    p.tile_lists = nullptr;
+    p.n_one = p.n_rest = 0;
     p.device = -1;
 }
 
@@ -680,6 +697,60 @@ static void pick_stage(pb_plan& p, const int* h) {
     p.max_units = units | 1;
 }
 
+// Double-fisheye source: which tiles see exactly one lens at unit blend weights (same test as the
+// kernel's: the 64 rows of the tile, rows past the image edge repeating the last one), in the
+// order the kernel rasters them.  fp: the plan's footprints on the host.
+static void classify_tiles(pb_plan& p, const int4* fp, cudaStream_t st) {
+    if (p.src.kind != PB_KIND_DOUBLE || p.tile_lists) return;
+    const int tx = tiles_x(p), ty = tiles_y(p), n_tiles = tx * ty, H = p.out.H;
+    std::vector<double> rows(4 * (size_t)H);
+    if (cudaMemcpyAsync(rows.data(), p.tables + 2 * (size_t)p.out.W, rows.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                        st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;
+    }
+    std::vector<char> unit_rows(ty);  // every row of the tile row has both weights exactly 1
+    for (int t = 0; t < ty; ++t) {
+        bool unit = true;
+        for (int r = t * kTileH; r < (t + 1) * kTileH; ++r) {
+            const int i = r < H ? r : H - 1;
+            unit = unit && rows[4 * (size_t)i + 2] == 1.0 && rows[4 * (size_t)i + 3] == 1.0;
+        }
+        unit_rows[t] = unit;
+    }
+    std::vector<int> one, rest;
+    for (int b = 0; b < n_tiles; ++b) {
+        int x, y;
+        if (p.raster_band > 0) {  // as remap_tiled_kernel walks them
+            const int per_band = p.raster_band * tx, band = b / per_band, within = b - band * per_band;
+            const int bh = std::min(p.raster_band, ty - band * p.raster_band);
+            x = within / bh;
+            y = band * p.raster_band + (within - x * bh);
+        } else {
+            y = b / tx;
+            x = b - y * tx;
+        }
+        const int t = y * tx + x;
+        const bool l = fp[2 * t].z > 0, r = fp[2 * t + 1].z > 0;
+        ((l != r) && unit_rows[y] ? one : rest).push_back(t);
+    }
+    int* lists = nullptr;
+    if (cudaMalloc((void**)&lists, sizeof(int) * n_tiles) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;
+    }
+    one.insert(one.end(), rest.begin(), rest.end());
+    if (cudaMemcpyAsync(lists, one.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaFree(lists);
+        return;
+    }
+    p.tile_lists = lists;
+    p.n_rest = (int)rest.size();
+    p.n_one = n_tiles - p.n_rest;
+}
+
 static void tune_stage(pb_plan& p, cudaStream_t st) {
     if (p.desc.channels != 3) return;
     int h[kProbeInts] = {0};
@@ -701,6 +772,7 @@ static void tune_stage(pb_plan& p, cudaStream_t st) {
                 if (fits && units > h[kProbeSizeBins]) h[kProbeSizeBins] = units;
             }
             pick_stage(p, h);
+            classify_tiles(p, host, st);
             // single-frame kernel: one buffer holds every rectangle of a tile; size it for 99.5 % of the tiles
             const int nslot = p.src.kind == PB_KIND_DOUBLE ? 2 : 1;
             const int n_tiles = n_entries / nslot;
@@ -914,6 +986,23 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
                 else
                     e = launch_sep1_one<PB_KIND_DOUBLE, 2>(a, st);
             }
+            else if (sep && whole && multi && dbl && p.tile_lists && tables == p.tables && !class_split_off()) {
+                // a batch through a double-fisheye source: the tiles that see one lens (small
+                // footprints; three CTAs per SM, each with several frames in flight) and the rest
+                // (two big rectangles per frame: two CTAs per SM with a stage area twice as large)
+                a.n_buffers = 2;
+                a.n_out = 2;
+                a.tile_list = p.tile_lists + p.n_one;
+                a.n_list = p.n_rest;
+                a.stage_bytes = env_int("PB_REST_KIB", 50) * 1024;
+                e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 2>(a, st);
+                if (e == cudaSuccess) {
+                    a.tile_list = p.tile_lists;
+                    a.n_list = p.n_one;
+                    a.stage_bytes = env_int("PB_ONE_BYTES", 31 * 1024);
+                    e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 1>(a, st);
+                }
+            }
             else
                 e = launch_tiled(a, sep, st);
             if (e != cudaSuccess) return cuda_fail(e, "tiled remap launch");
@@ -1033,6 +1122,7 @@ int pb_plan_remap_rows_u8(const pb_plan* plan, const uint8_t* src, uint8_t* dst_
 void pb_plan_destroy(pb_plan* plan) {
     if (!plan) return;
     if (plan->tables) cudaFree(plan->tables);
+    if (plan->tile_lists) cudaFree(plan->tile_lists);
     delete plan;
 }
 

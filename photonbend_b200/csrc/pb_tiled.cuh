@@ -86,6 +86,8 @@ struct TiledArgs {
 #ifdef PB_EXPERIMENTS
     int debug;  // timing experiments (wrong output): 1 = no loads / waits, 2 = no gather, 4 = no stores
 #endif
+    const int* tile_list;  // non-null: CTA b remaps tile tile_list[b] (a class of tiles, in raster order; n_list CTAs)
+    int n_list;
     const int4* tile_fp;  // separable: per (tile, slot) footprint {by0, xb0, nbox, all_valid | need_bytes << 1}
     const int4* sep1_tab; // separable: the same per (tile in launch order, slot), pre-decoded (pb_sep1.cuh)
     const double* sep1_col;  // single-frame kernel: per-tile column / row table slices (pb_sep1_slices_kernel)
@@ -188,6 +190,35 @@ __device__ __forceinline__ unsigned blend_px_weighted(unsigned a, double wa, uns
 #pragma unroll
     for (int c = 0; c < 3; ++c)
         r |= (unsigned)blend_u8((a >> (8 * c)) & 0xffu, wa, (b >> (8 * c)) & 0xffu, wb) << (8 * c);
+    return r;
+}
+
+// Fixed-point short cut of the weighted blend (projection.py:459).  The reference truncates
+// t = fl(fl(a*wa) + fl(b*wb)), a and b bytes; t is within 1e-13 of the real T = a*wa + b*wb.  With
+// the weights rounded to 24 fractional bits, a*ia + b*ib is within 255 units of T * 2^24 (half a
+// unit per weight, a, b <= 255) and fits an unsigned word while both weights are >= 0 and their
+// sum is <= 1 + 2^-8 (inside the blend band they add up to 1).  So wherever the fixed-point
+// fraction is more than 256 units away from an integer its integer part -- the top byte of the
+// word -- IS trunc(t); the other ~3e-5 of the channels, and rows whose weights do not qualify (the
+// half-degree "safety" strip with its negative weight), take the float64 expression itself.
+constexpr int kFixShift = 24;
+constexpr unsigned kFixGuard = 257;
+__device__ __forceinline__ bool fix_weights(double wa, double wb, unsigned& ia, unsigned& ib) {
+    const bool ok = wa >= 0.0 && wb >= 0.0 && wa + wb <= 1.00390625;  // false for NaN
+    ia = ok ? (unsigned)__double2int_rn(wa * (double)(1 << kFixShift)) : 0u;
+    ib = ok ? (unsigned)__double2int_rn(wb * (double)(1 << kFixShift)) : 0u;
+    return ok;
+}
+__device__ __forceinline__ unsigned blend_px_fix(unsigned a, unsigned ia, double wa, unsigned b, unsigned ib, double wb) {
+    unsigned t[3], u[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        t[c] = __byte_perm(a, 0, 0x4440 + c) * ia + __byte_perm(b, 0, 0x4440 + c) * ib;
+        // fraction to the top of the word, minus the guard: in range iff guard <= fraction <= 2^24 - guard - 1
+        u[c] = t[c] * 256u - (kFixGuard << 8);
+    }
+    unsigned r = __byte_perm(__byte_perm(t[0], t[1], 0x4473), t[2], 0x4710);  // the three top bytes
+    if (max(max(u[0], u[1]), u[2]) >= ((1u << kFixShift) - 2u * kFixGuard) << 8) r = blend_px_weighted(a, wa, b, wb);
     return r;
 }
 
@@ -381,12 +412,25 @@ __device__ __noinline__ void direct_tile(const TiledArgs& a, const int* xy_scrat
 }
 
 // MODE: 0 = generic per-pixel rays (any output, any rotations), 1 = separable tables
-template <int OUT_KIND, int SRC_KIND, int MODE>
-__global__ void __launch_bounds__(kTileThreads, (MODE == 1) ? ((SRC_KIND == PB_KIND_DOUBLE) ? 3 : 5) : 2)
+// CLS (separable double-fisheye source, batches; the plan sorts the tiles into two launches):
+//   0 = any tile;
+//   1 = tiles that see exactly one lens at unit weights (3 of 4 tiles of a 195-degree pair): one
+//       slot, chosen per tile, small footprints, many frames in flight at 3-4 CTAs per SM;
+//   2 = the rest (both lenses, blend band): the code of class 0 at 2 CTAs per SM, i.e. with a
+//       stage area large enough to keep several frames of their two big rectangles in flight.
+#ifndef PB_ONE_LENS_CTAS
+#define PB_ONE_LENS_CTAS 3
+#endif
+constexpr int tiled_min_ctas(int src_kind, int mode, int cls) {
+    return mode != 1 ? 2 : src_kind != PB_KIND_DOUBLE ? 5 : cls == 2 ? 2 : cls == 1 ? PB_ONE_LENS_CTAS : 3;
+}
+template <int OUT_KIND, int SRC_KIND, int MODE, int CLS = 0>
+__global__ void __launch_bounds__(kTileThreads, tiled_min_ctas(SRC_KIND, MODE, CLS))
 remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
-    constexpr int NSLOT = (SRC_KIND == PB_KIND_DOUBLE) ? 2 : 1;
-    constexpr int S1 = NSLOT - 1;  // index of the second slot (aliases the first when there is none)
     constexpr bool DBL = (SRC_KIND == PB_KIND_DOUBLE);
+    constexpr bool ONE = DBL && MODE == 1 && CLS == 1;  // one lens per tile, picked at run time
+    constexpr int NSLOT = (DBL && !ONE) ? 2 : 1;
+    constexpr int S1 = NSLOT - 1;  // index of the second slot (aliases the first when there is none)
     constexpr bool WGT_IN_SMEM = DBL && MODE == 0;  // per-pixel weights live in shared memory
 
     extern __shared__ __align__(128) unsigned char smem[];
@@ -410,7 +454,11 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     // CTA pulled into L2 is still there when its neighbours ask for it.  Bands of raster_band tile
     // rows, walked column by column (the last band may be shorter).
     int tile_x, tile_y;
-    if (a.raster_band > 0) {
+    if (a.tile_list != nullptr) {
+        const int t = __ldg(a.tile_list + blockIdx.x);
+        tile_y = t / a.tiles_x;
+        tile_x = t - tile_y * a.tiles_x;
+    } else if (a.raster_band > 0) {
         const int per_band = a.raster_band * a.tiles_x;
         const int band = blockIdx.x / per_band, within = blockIdx.x - band * per_band;
         const int bh = min(a.raster_band, a.tiles_y - band * a.raster_band);
@@ -450,9 +498,17 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     double wrow[kRowsPerThread][2];  // separable double source: blend weights per row
     bool unit_weights = true;        // block-uniform: no pixel of the tile needs a weighted blend
     int4 fpv[NSLOT];
+    bool right_lens = false;  // ONE: the tile's lens
     if (MODE == 1) {
+        if (ONE) {
+            const int4 f0 = __ldg(a.tile_fp + (tile_y * a.tiles_x + tile_x) * 2);
+            const int4 f1 = __ldg(a.tile_fp + (tile_y * a.tiles_x + tile_x) * 2 + 1);
+            right_lens = f0.z == 0;
+            fpv[0] = right_lens ? f1 : f0;
+        } else {
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s) fpv[s] = __ldg(a.tile_fp + (tile_y * a.tiles_x + tile_x) * NSLOT + s);
+            for (int s = 0; s < NSLOT; ++s) fpv[s] = __ldg(a.tile_fp + (tile_y * a.tiles_x + tile_x) * NSLOT + s);
+        }
         // per-tile slices of the tables in the layout of pb_sep1_slices_kernel: for each of its 4
         // columns a warp reads 128 contiguous bytes (the [W][2] table read at a 64-byte stride cost
         // ~12 L1 wavefronts per LDG.128), rows past the image edge repeat the last row
@@ -463,7 +519,10 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 #pragma unroll
             for (int q = 0; q < kRowsPerThread; ++q) {
                 const int r = tile_y * kTileH + rg + q * kRowGroups;
-                if (DBL) {
+                if (ONE) {
+                    r01[q].x = __ldg(a.sep1_row + 4 * r + (right_lens ? 1 : 0));
+                    r01[q].y = 0.0;
+                } else if (DBL) {
                     const double2* __restrict__ row = reinterpret_cast<const double2*>(a.sep1_row) + 2 * r;
                     r01[q] = __ldg(row);
                     const double2 r23 = __ldg(row + 1);
@@ -476,11 +535,17 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             }
         }
         // barrier init + zeroed tails visible; and: is every blend weight of the tile exactly 1?
-        if (DBL) {
+        if (DBL && !ONE) {
             bool mine = true;
 #pragma unroll
             for (int q = 0; q < kRowsPerThread; ++q) mine = mine && wrow[q][0] == 1.0 && wrow[q][1] == 1.0;
             unit_weights = __syncthreads_and(mine);
+#ifdef PB_EXPERIMENTS
+            // timing experiments: leave out a class of tiles (16: one lens, 32: both lenses with unit
+            // weights, 64: blend band)
+            const int cls = (fpv[0].z > 0 && fpv[S1].z > 0) ? (unit_weights ? 32 : 64) : 16;
+            if (a.debug & cls) return;
+#endif
         } else {
             __syncthreads();
         }
@@ -522,7 +587,8 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     // rectangle of slot s: rows [by0, by0 + 16*nbox), bytes [xb0, xb0 + pitch) of each row
     int by0[NSLOT], xb0[NSLOT], nbox[NSLOT], pitch[NSLOT];
     bool all_valid[NSLOT];
-    bool staged = true;
+    bool staged = true;  // every rectangle fits a stage buffer (what the (frame, slot) item loop needs)
+    bool wide = false;   // some rectangle is wider than any tensor map: cannot be staged at all
 #pragma unroll
     for (int s = 0; s < NSLOT; ++s) {
         int need_bytes = 0;
@@ -552,6 +618,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         const int units = stage_units(need_bytes);
         pitch[s] = 16 * units;
         const int bytes = nbox[s] * kBoxRows * pitch[s];
+        if (units > a.max_units) wide = true;
         if (units > a.max_units || bytes > a.stage_bytes) staged = false;
         if (a.probe != nullptr && tid == 0) {
             const bool fits = units <= kMaxStageUnits;
@@ -560,10 +627,6 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
         }
     }
     if (a.probe != nullptr) return;
-    if (!staged) {  // block-uniform
-        direct_tile<OUT_KIND, SRC_KIND, MODE>(a, xy_scratch, w_scratch, out_tiles, x0, y0);
-        return;
-    }
 
     // ---------------------------------------------------------------- 3. stage (issued first: the loads fly while the offsets are resolved)
     // items = (frame, active slot) pairs, in order; item t uses stage buffer t % n_buffers
@@ -605,8 +668,14 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 #ifdef PB_EXPERIMENTS
     if (a.debug >> 8) n_groups = min(n_groups, a.debug >> 8);
 #endif
-    const bool lean = unit_weights && n_act >= 1 && n_groups >= a.lean_min_groups &&
-                      (a.n_out == 2 || a.n_frames == 1) && !dbg_noload && !dbg_nogather && !dbg_nostore;
+    // (separable double source: tiles of the blend band run it too, with the per-row weighted blend)
+    // (the lean loop only needs one frame's rectangles to fit the whole stage area)
+    const bool lean = (unit_weights || (MODE == 1 && DBL && !ONE)) && n_act >= 1 && n_groups >= a.lean_min_groups &&
+                      !wide && (a.n_out == 2 || a.n_frames == 1) && !dbg_noload && !dbg_nogather && !dbg_nostore;
+    if (!staged && !lean) {  // block-uniform
+        direct_tile<OUT_KIND, SRC_KIND, MODE>(a, xy_scratch, w_scratch, out_tiles, x0, y0);
+        return;
+    }
     auto issue_group = [&](int f, int g) {  // one thread: every rectangle of frame f into group g
         unsigned char* base = stages + g * group_bytes + 128;
         ptx::mbarrier_arrive_expect_tx(&sh->bar[g], (unsigned)(rect0 + rect1));
@@ -648,8 +717,9 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     if (MODE == 1) {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
-            const int w = DBL ? (s ? a.src.wr : a.src.wl) : a.src.W;
-            const double cx = DBL ? (s ? a.src.cxr : a.src.cxl) : a.src.cx;
+            const bool right = ONE ? right_lens : (s != 0);  // right half of a double image: mirrored columns
+            const int w = DBL ? (right ? a.src.wr : a.src.wl) : a.src.W;
+            const double cx = DBL ? (right ? a.src.cxr : a.src.cxl) : a.src.cx;
             const int origin = by0[s] * pitch[s] + xb0[s];
             if (nbox[s] == 0) {  // nothing of this slot is visible from the tile
 #pragma unroll
@@ -662,7 +732,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                         double fx, fy;
                         camera_fxy(cs[k].x, cs[k].y, s ? r01[q].y : r01[q].x, a.src.cy, cx, fx, fy);
                         int px = trunc_abs(fx);
-                        if (s) px = a.src.W - 1 - px;
+                        if (right) px = a.src.W - 1 - px;
                         loc[s][q * 4 + k] = trunc_abs(fy) * pitch[s] + (px * 3 - origin);
                     }
             } else {
@@ -673,7 +743,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                         double fx, fy;
                         camera_fxy(cs[k].x, cs[k].y, s ? r01[q].y : r01[q].x, a.src.cy, cx, fx, fy);
                         int px = trunc_abs(fx);
-                        if (s) px = a.src.W - 1 - px;
+                        if (right) px = a.src.W - 1 - px;
                         const int off = trunc_abs(fy) * pitch[s] + (px * 3 - origin);
                         loc[s][q * 4 + k] = inside_image(fx, fy, w, a.src.H) ? off : ztail;
                     }
@@ -711,24 +781,61 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                 adr[s][p] = stages_sa + (unsigned)(rel & ~3);
                 shf[s][p] = (unsigned)rel << 3;
             }
+        // blend band: per row of this thread, 0 = unit weights (exact byte add), 1 = fixed-point
+        // short cut with float64 fall-back, 2 = float64 only
+        unsigned wfix[kRowsPerThread][2];
+        int wmode[kRowsPerThread];
+#pragma unroll
+        for (int q = 0; q < kRowsPerThread; ++q) {
+            wfix[q][0] = wfix[q][1] = 0;
+            wmode[q] = 0;
+            if (MODE == 1 && DBL && !ONE && !unit_weights && !(wrow[q][0] == 1.0 && wrow[q][1] == 1.0))
+                wmode[q] = fix_weights(wrow[q][0], wrow[q][1], wfix[q][0], wfix[q][1]) ? 1 : 2;
+        }
         __syncthreads();  // the groups' zero bytes are in place
-        auto frame_loop = [&](auto ACT) {
+        auto frame_loop = [&](auto ACT, auto WGT) {
             constexpr int act = decltype(ACT)::value;  // 1: slot 0 only, 2: slot 1 only, 3: both
+            constexpr bool wgt = decltype(WGT)::value;  // some row of the tile has a weighted blend
             int g = 0;
             unsigned parity = 0;
             for (int f = 0; f < a.n_frames; ++f) {
                 const unsigned goff = (unsigned)(g * group_bytes);
                 ptx::mbarrier_wait_sa(bar_sa + 8 * g, parity);
                 unsigned v[kPxPerThread];
-                if (act & 1) {
-#pragma unroll
-                    for (int p = 0; p < kPxPerThread; ++p) v[p] = PB_LEAN_PICK(adr[0][p], goff, shf[0][p]);
-                }
-                if (act & 2) {
+                if (wgt) {
+                    unsigned w[kPxPerThread];
 #pragma unroll
                     for (int p = 0; p < kPxPerThread; ++p) {
-                        const unsigned w = PB_LEAN_PICK(adr[S1][p], goff, shf[S1][p]);
-                        v[p] = (act & 1) ? __vadd4(v[p], w) : w;
+                        v[p] = (act & 1) ? PB_LEAN_PICK(adr[0][p], goff, shf[0][p]) : 0u;
+                        w[p] = (act & 2) ? PB_LEAN_PICK(adr[S1][p], goff, shf[S1][p]) : 0u;
+                    }
+#pragma unroll
+                    for (int q = 0; q < kRowsPerThread; ++q) {
+                        if (wmode[q] == 0) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) v[q * 4 + k] = __vadd4(v[q * 4 + k], w[q * 4 + k]);
+                        } else if (wmode[q] == 1) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                v[q * 4 + k] = blend_px_fix(v[q * 4 + k], wfix[q][0], wrow[q][0], w[q * 4 + k], wfix[q][1],
+                                                            wrow[q][1]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                v[q * 4 + k] = blend_px_weighted(v[q * 4 + k], wrow[q][0], w[q * 4 + k], wrow[q][1]);
+                        }
+                    }
+                } else {
+                    if (act & 1) {
+#pragma unroll
+                        for (int p = 0; p < kPxPerThread; ++p) v[p] = PB_LEAN_PICK(adr[0][p], goff, shf[0][p]);
+                    }
+                    if (act & 2) {
+#pragma unroll
+                        for (int p = 0; p < kPxPerThread; ++p) {
+                            const unsigned w = PB_LEAN_PICK(adr[S1][p], goff, shf[S1][p]);
+                            v[p] = (act & 1) ? __vadd4(v[p], w) : w;
+                        }
                     }
                 }
                 const unsigned o = out_sa + (f & 1) * out_flip;
@@ -749,9 +856,13 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                 }
             }
         };
-        if (n_act == 2) frame_loop(std::integral_constant<int, 3>{});
-        else if (first == 0) frame_loop(std::integral_constant<int, 1>{});
-        else frame_loop(std::integral_constant<int, 2>{});
+        if (MODE == 1 && DBL && !ONE && !unit_weights) {
+            if (n_act == 2) frame_loop(std::integral_constant<int, 3>{}, std::true_type{});
+            else if (first == 0) frame_loop(std::integral_constant<int, 1>{}, std::true_type{});
+            else frame_loop(std::integral_constant<int, 2>{}, std::true_type{});
+        } else if (n_act == 2) frame_loop(std::integral_constant<int, 3>{}, std::false_type{});
+        else if (first == 0) frame_loop(std::integral_constant<int, 1>{}, std::false_type{});
+        else frame_loop(std::integral_constant<int, 2>{}, std::false_type{});
         if (tid == 0) ptx::bulk_wait_read0();
         return;
     }
