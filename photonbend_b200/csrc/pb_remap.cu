@@ -988,7 +988,7 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
             }
             else if (sep && whole && multi && dbl && p.tile_lists && tables == p.tables && !class_split_off()) {
                 // a batch through a double-fisheye source: the tiles that see one lens (small
-                // footprints; three CTAs per SM, each with several frames in flight) and the rest
+                // footprints; four CTAs per SM, each with several frames in flight) and the rest
                 // (two big rectangles per frame: two CTAs per SM with a stage area twice as large)
                 a.n_buffers = 2;
                 a.n_out = 2;
@@ -999,7 +999,7 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
                 if (e == cudaSuccess) {
                     a.tile_list = p.tile_lists;
                     a.n_list = p.n_one;
-                    a.stage_bytes = env_int("PB_ONE_BYTES", 31 * 1024);
+                    a.stage_bytes = env_int("PB_ONE_BYTES", 21 * 1024);  // four CTAs per SM
                     e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 1>(a, st);
                 }
             }

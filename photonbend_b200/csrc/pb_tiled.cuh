@@ -415,11 +415,11 @@ __device__ __noinline__ void direct_tile(const TiledArgs& a, const int* xy_scrat
 // CLS (separable double-fisheye source, batches; the plan sorts the tiles into two launches):
 //   0 = any tile;
 //   1 = tiles that see exactly one lens at unit weights (3 of 4 tiles of a 195-degree pair): one
-//       slot, chosen per tile, small footprints, many frames in flight at 3-4 CTAs per SM;
+//       slot, chosen per tile, small footprints, many frames in flight at 4 CTAs per SM;
 //   2 = the rest (both lenses, blend band): the code of class 0 at 2 CTAs per SM, i.e. with a
 //       stage area large enough to keep several frames of their two big rectangles in flight.
 #ifndef PB_ONE_LENS_CTAS
-#define PB_ONE_LENS_CTAS 3
+#define PB_ONE_LENS_CTAS 4
 #endif
 constexpr int tiled_min_ctas(int src_kind, int mode, int cls) {
     return mode != 1 ? 2 : src_kind != PB_KIND_DOUBLE ? 5 : cls == 2 ? 2 : cls == 1 ? PB_ONE_LENS_CTAS : 3;
@@ -714,6 +714,9 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     // ---------------------------------------------------------------- 1. resolve (separable) -> byte offsets
     // loc = byte offset of the pixel inside the staged rectangle of its slot (ztail: no source)
     int loc[NSLOT][kPxPerThread];
+    // "no source pixel": the zeroed tail of the stage buffer in the item loop; the lean loop may
+    // stage rectangles larger than a stage buffer, where ztail is a real offset, so it marks with -1
+    const int no_px = lean ? -1 : ztail;
     if (MODE == 1) {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
@@ -723,7 +726,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             const int origin = by0[s] * pitch[s] + xb0[s];
             if (nbox[s] == 0) {  // nothing of this slot is visible from the tile
 #pragma unroll
-                for (int p = 0; p < kPxPerThread; ++p) loc[s][p] = ztail;
+                for (int p = 0; p < kPxPerThread; ++p) loc[s][p] = no_px;
             } else if (all_valid[s]) {  // every pixel lands inside the source: no bounds tests
 #pragma unroll
                 for (int q = 0; q < kRowsPerThread; ++q)
@@ -745,7 +748,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                         int px = trunc_abs(fx);
                         if (right) px = a.src.W - 1 - px;
                         const int off = trunc_abs(fy) * pitch[s] + (px * 3 - origin);
-                        loc[s][q * 4 + k] = inside_image(fx, fy, w, a.src.H) ? off : ztail;
+                        loc[s][q * 4 + k] = inside_image(fx, fy, w, a.src.H) ? off : no_px;
                     }
             }
         }
@@ -756,7 +759,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 #pragma unroll
             for (int p = 0; p < kPxPerThread; ++p) {
                 const int v = xy_scratch[(s * kPxPerThread + p) * kTileThreads + tid];
-                loc[s][p] = (v >= 0) ? (v >> 16) * pitch[s] + (v & 0xffff) * 3 - origin : ztail;
+                loc[s][p] = (v >= 0) ? (v >> 16) * pitch[s] + (v & 0xffff) * 3 - origin : no_px;
             }
         }
     }
@@ -777,7 +780,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
 #pragma unroll
             for (int p = 0; p < kPxPerThread; ++p) {
                 const int l = loc[s][p];
-                const int rel = (l == ztail) ? 0 : l + 128 + (s ? rect0 : 0);
+                const int rel = (l == no_px) ? 0 : l + 128 + (s ? rect0 : 0);
                 adr[s][p] = stages_sa + (unsigned)(rel & ~3);
                 shf[s][p] = (unsigned)rel << 3;
             }

@@ -307,6 +307,41 @@ def test_tiled_fast_path_mid_size_batches(torch_cuda, src_kind):
         (src_kind, n_bad1, max_abs1)
 
 
+@pytest.mark.parametrize("fov_deg", [195, 180, 181, 210, 170, 250])
+def test_double_source_batches_blend_band(torch_cuda, fov_deg, monkeypatch):
+    """Batches through a double-fisheye source (csrc/pb_tiled.cuh: two launches by tile class,
+    blend band through the guarded fixed-point blend) on frames chosen to sit ON the blend's
+    truncation boundaries: flat frames (left == right, weights adding up to 1 -> the float64 sum is
+    an integer up to its last bits), black frames, a ramp, and noise; several sensor fovs (180:
+    zero-width band, division by zero in the weights; 170: negative range), against the NumPy oracle."""
+    torch = torch_cuda
+    from oracle import numpy_port
+
+    sg = {"kind": "double", "height": 336, "width": 672, "lens": "equidistant", "fov": case_matrix.rad(fov_deg)}
+    og = {"kind": "equirect", "height": 336 + 16, "width": 672 + 32}
+    rng = np.random.default_rng(fov_deg)
+    h, w = sg["height"], sg["width"]
+    ramp = (np.arange(h * w * 3, dtype=np.int64).reshape(h, w, 3) // 7 % 256).astype(np.uint8)
+    frames = np.stack([
+        np.full((h, w, 3), 200, np.uint8),
+        np.zeros((h, w, 3), np.uint8),
+        np.full((h, w, 3), 255, np.uint8),
+        ramp,
+        case_matrix.case_image(sg, 500 + fov_deg),
+        (rng.integers(0, 4, (h, w, 3)) * 85).astype(np.uint8),
+    ])
+    want = [numpy_port.remap(og, (), sg, f) for f in frames]
+    dev = torch.from_numpy(frames).cuda()
+    for env in ({}, {"PB_ONE_BYTES": "4096", "PB_REST_KIB": "8"}, {"PB_CLASS_SPLIT": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = helpers.product_image(sg, dev).process_coordinate_map(helpers.product_map(og, ())).cpu().numpy()
+        for k in range(len(frames)):
+            assert np.array_equal(out[k], want[k]), (fov_deg, env, k, mismatch_report(out[k], want[k]))
+        for k in env:
+            monkeypatch.delenv(k)
+
+
 def _mid_size_geometries():
     """Every lens on both sides at a size that takes the tiled (TMA-staged) path."""
     rad = case_matrix.rad
