@@ -87,6 +87,11 @@ typedef struct pb_remap_desc {
 int pb_version(void);
 const char *pb_last_error(void);
 
+/* Kernels this library has launched in this process so far (every grid counts once; a batch
+ * through a double-fisheye source is two grids, one per tile class).  For benchmarks that have to
+ * state how many of their own kernels ran inside a timed region. */
+int64_t pb_kernel_launches(void);
+
 /* Width of the image a geometry produces: 2*(width/2) for PB_KIND_DOUBLE (projection.py:389-397),
  * width otherwise. */
 int32_t pb_output_width(const pb_image_desc *out);

@@ -28,6 +28,7 @@ PB_ERR_TOO_MANY_ROTATIONS = 4
 EXPORTS = (
     "pb_version",
     "pb_last_error",
+    "pb_kernel_launches",
     "pb_output_width",
     "pb_remap_u8",
     "pb_plan_create",
@@ -88,6 +89,8 @@ def load():
     lib.pb_version.argtypes = []
     lib.pb_last_error.restype = ctypes.c_char_p
     lib.pb_last_error.argtypes = []
+    lib.pb_kernel_launches.restype = ctypes.c_int64
+    lib.pb_kernel_launches.argtypes = []
     lib.pb_output_width.restype = i32
     lib.pb_output_width.argtypes = [ctypes.POINTER(ImageDesc)]
     lib.pb_remap_u8.restype = ctypes.c_int

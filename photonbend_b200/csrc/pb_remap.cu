@@ -4,6 +4,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
 //        -Xcompiler -fPIC,-ffp-contract=off -shared -Iinclude -o libpbremap.so pb_remap.cu
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,9 @@ namespace pb {
 // ------------------------------------------------------------------------------------ errors
 
 static thread_local std::string g_last_error;
+// kernels this library has launched in this process (pb_kernel_launches)
+static std::atomic<long long> g_kernel_launches{0};
+#define PB_COUNT_LAUNCH() g_kernel_launches.fetch_add(1, std::memory_order_relaxed)
 
 static int fail(int code, const std::string& msg) {
     g_last_error = msg;
@@ -406,10 +410,10 @@ static void launch_generic_c(const RemapArgs& a, cudaStream_t st) {
     dim3 block(32, 8);
     dim3 grid((a.out.W + block.x - 1) / block.x, (a.row_end - a.row_begin + block.y - 1) / block.y);
     switch (a.src.C) {
-        case 1: remap_generic_kernel<OUT_KIND, SRC_KIND, 1><<<grid, block, 0, st>>>(a); break;
-        case 2: remap_generic_kernel<OUT_KIND, SRC_KIND, 2><<<grid, block, 0, st>>>(a); break;
-        case 3: remap_generic_kernel<OUT_KIND, SRC_KIND, 3><<<grid, block, 0, st>>>(a); break;
-        default: remap_generic_kernel<OUT_KIND, SRC_KIND, 4><<<grid, block, 0, st>>>(a); break;
+        case 1: remap_generic_kernel<OUT_KIND, SRC_KIND, 1><<<grid, block, 0, st>>>(a); PB_COUNT_LAUNCH(); break;
+        case 2: remap_generic_kernel<OUT_KIND, SRC_KIND, 2><<<grid, block, 0, st>>>(a); PB_COUNT_LAUNCH(); break;
+        case 3: remap_generic_kernel<OUT_KIND, SRC_KIND, 3><<<grid, block, 0, st>>>(a); PB_COUNT_LAUNCH(); break;
+        default: remap_generic_kernel<OUT_KIND, SRC_KIND, 4><<<grid, block, 0, st>>>(a); PB_COUNT_LAUNCH(); break;
     }
 }
 
@@ -425,9 +429,9 @@ static void launch_generic_s(const RemapArgs& a, cudaStream_t st) {
 template <int OUT_KIND>
 static void launch_direct_s(const RemapArgs& a, dim3 grid, cudaStream_t st) {
     switch (a.src.kind) {
-        case PB_KIND_CAMERA: remap_direct_kernel<OUT_KIND, PB_KIND_CAMERA><<<grid, 256, 0, st>>>(a); break;
-        case PB_KIND_DOUBLE: remap_direct_kernel<OUT_KIND, PB_KIND_DOUBLE><<<grid, 256, 0, st>>>(a); break;
-        default: remap_direct_kernel<OUT_KIND, PB_KIND_EQUIRECT><<<grid, 256, 0, st>>>(a); break;
+        case PB_KIND_CAMERA: remap_direct_kernel<OUT_KIND, PB_KIND_CAMERA><<<grid, 256, 0, st>>>(a); PB_COUNT_LAUNCH(); break;
+        case PB_KIND_DOUBLE: remap_direct_kernel<OUT_KIND, PB_KIND_DOUBLE><<<grid, 256, 0, st>>>(a); PB_COUNT_LAUNCH(); break;
+        default: remap_direct_kernel<OUT_KIND, PB_KIND_EQUIRECT><<<grid, 256, 0, st>>>(a); PB_COUNT_LAUNCH(); break;
     }
 }
 
@@ -454,10 +458,10 @@ static void launch_gather_c(const SrcGeom& s, double* map, long long n, const un
     const int block = 256;
     const unsigned grid = (unsigned)((n + block - 1) / block);
     switch (s.C) {
-        case 1: gather_from_map_kernel<SRC_KIND, 1><<<grid, block, 0, st>>>(s, map, n, sp, dst); break;
-        case 2: gather_from_map_kernel<SRC_KIND, 2><<<grid, block, 0, st>>>(s, map, n, sp, dst); break;
-        case 3: gather_from_map_kernel<SRC_KIND, 3><<<grid, block, 0, st>>>(s, map, n, sp, dst); break;
-        default: gather_from_map_kernel<SRC_KIND, 4><<<grid, block, 0, st>>>(s, map, n, sp, dst); break;
+        case 1: gather_from_map_kernel<SRC_KIND, 1><<<grid, block, 0, st>>>(s, map, n, sp, dst); PB_COUNT_LAUNCH(); break;
+        case 2: gather_from_map_kernel<SRC_KIND, 2><<<grid, block, 0, st>>>(s, map, n, sp, dst); PB_COUNT_LAUNCH(); break;
+        case 3: gather_from_map_kernel<SRC_KIND, 3><<<grid, block, 0, st>>>(s, map, n, sp, dst); PB_COUNT_LAUNCH(); break;
+        default: gather_from_map_kernel<SRC_KIND, 4><<<grid, block, 0, st>>>(s, map, n, sp, dst); PB_COUNT_LAUNCH(); break;
     }
 }
 
@@ -518,6 +522,7 @@ static cudaError_t launch_tiled_one(const TiledArgs& a, cudaStream_t st) {
     const int grid = a.tile_list ? a.n_list : a.tiles_x * a.tiles_y;
     if (grid <= 0) return cudaSuccess;
     remap_tiled_kernel<OUT_KIND, SRC_KIND, MODE, CLS><<<grid, kTileThreads, smem, st>>>(a);
+    PB_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -576,6 +581,7 @@ static cudaError_t launch_sep1_one(const TiledArgs& a, cudaStream_t st) {
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
     remap_sep1_kernel<SRC_KIND, NB><<<grid, kTileThreads, smem, st>>>(a);
+    PB_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -846,6 +852,7 @@ static void tune_stage(pb_plan& p, cudaStream_t st) {
 static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st) {
     const int n = p.out.W > p.out.H ? p.out.W : p.out.H;
     pb_tables_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.out, p.src, tables, tables + 2 * (size_t)p.out.W);
+    PB_COUNT_LAUNCH();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     TiledArgs a;
@@ -857,6 +864,7 @@ static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st
     const int n_entries = footprint_entries(p);
     pb_footprint_kernel<<<(n_entries + 7) / 8, 256, 0, st>>>(a, const_cast<int4*>(footprint_table(p, tables)),
                                                            tiles_x(p), n_entries);
+    PB_COUNT_LAUNCH();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int n_tiles = tiles_x(p) * tiles_y(p);
@@ -864,6 +872,7 @@ static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st
                                                               const_cast<int4*>(sep1_table(p, tables)), tiles_x(p),
                                                               tiles_y(p), p.raster_band,
                                                               p.src.kind == PB_KIND_DOUBLE ? 2 : 1);
+    PB_COUNT_LAUNCH();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int n_slice = std::max(tiles_x(p) * kTileW, tiles_y(p) * kTileH);
@@ -871,6 +880,7 @@ static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st
                                                                const_cast<double*>(sep1_col(p, tables)),
                                                                const_cast<double*>(sep1_row(p, tables)), p.out.W, p.out.H,
                                                                tiles_x(p), tiles_y(p), (int)sep1_row_doubles(p));
+    PB_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -1038,6 +1048,8 @@ extern "C" {
 
 int pb_version(void) { return PB_ABI_VERSION; }
 
+int64_t pb_kernel_launches(void) { return (int64_t)g_kernel_launches.load(std::memory_order_relaxed); }
+
 const char* pb_last_error(void) { return g_last_error.c_str(); }
 
 int32_t pb_output_width(const pb_image_desc* out) {
@@ -1140,9 +1152,9 @@ int pb_materialize_map_f64(const pb_remap_desc* desc, double* map, void* stream)
     dim3 grid((g.W + block.x - 1) / block.x, (g.H + block.y - 1) / block.y);
     cudaStream_t st = (cudaStream_t)stream;
     switch (g.kind) {
-        case PB_KIND_CAMERA: materialize_map_kernel<PB_KIND_CAMERA><<<grid, block, 0, st>>>(g, rot, map); break;
-        case PB_KIND_DOUBLE: materialize_map_kernel<PB_KIND_DOUBLE><<<grid, block, 0, st>>>(g, rot, map); break;
-        default: materialize_map_kernel<PB_KIND_EQUIRECT><<<grid, block, 0, st>>>(g, rot, map); break;
+        case PB_KIND_CAMERA: materialize_map_kernel<PB_KIND_CAMERA><<<grid, block, 0, st>>>(g, rot, map); PB_COUNT_LAUNCH(); break;
+        case PB_KIND_DOUBLE: materialize_map_kernel<PB_KIND_DOUBLE><<<grid, block, 0, st>>>(g, rot, map); PB_COUNT_LAUNCH(); break;
+        default: materialize_map_kernel<PB_KIND_EQUIRECT><<<grid, block, 0, st>>>(g, rot, map); PB_COUNT_LAUNCH(); break;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "pb_materialize_map_f64 launch");
@@ -1160,6 +1172,7 @@ int pb_rotate_map_f64(const double matrix[9], double* map_in, double* map_out, i
     const long long blocks = (n_pixels + block - 1) / block;
     if (blocks > 0x7fffffffLL) return fail(PB_ERR_UNSUPPORTED, "pb_rotate_map_f64: map too large");
     rotate_map_kernel<<<(unsigned)blocks, block, 0, (cudaStream_t)stream>>>(m, map_in, map_out, n_pixels);
+    PB_COUNT_LAUNCH();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "pb_rotate_map_f64 launch");
     return PB_OK;

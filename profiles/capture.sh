@@ -12,7 +12,8 @@ python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_ref_${tag}.js
 python bench.py $small > $out/plain_${tag}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $out/launches_${tag}.csv \
     python bench.py $small > $out/ncu_launches_${tag}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:remap_tiled -s 4 -c 1 -f -o $out/prof_${tag}_cfg5_16frames \
+# (cfg5 steps are two grids of the tiled kernel, one per tile class: capture both of one step)
+ncu --set full --clock-control none --import-source on -k regex:remap_tiled -s 8 -c 2 -f -o $out/prof_${tag}_cfg5_16frames \
     python bench.py $small > $out/ncu_full_${tag}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:remap_tiled -s 4 -c 1 -f -o $out/prof_${tag}_T_16frames \
     python bench.py --workload T $small > $out/ncu_full_${tag}_T.log 2>&1
