@@ -474,7 +474,7 @@ def run_gpu(args):
             line["cpu_baseline"] = cpu
         if also:
             line["also"] = also
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -518,7 +518,30 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line: everything else that writes to fd 1 (NCCL's version banner,
+    library chatter of child processes) goes to stderr from here on."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -536,6 +559,7 @@ def main():
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch from the committed ncu capture (profiles/)")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
