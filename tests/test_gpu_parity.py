@@ -340,6 +340,12 @@ def test_double_source_batches_blend_band(torch_cuda, fov_deg, monkeypatch):
             assert np.array_equal(out[k], want[k]), (fov_deg, env, k, mismatch_report(out[k], want[k]))
         for k in env:
             monkeypatch.delenv(k)
+    # few tiles: a class of tiles may be empty (one tile; a band that sees both lenses everywhere)
+    for oh, ow in ((64, 32), (48, 80), (130, 96), (64, 704)):
+        og2 = {"kind": "equirect", "height": oh, "width": ow}
+        out = helpers.product_image(sg, dev[3:5]).process_coordinate_map(helpers.product_map(og2, ())).cpu().numpy()
+        for k in range(2):
+            assert np.array_equal(out[k], numpy_port.remap(og2, (), sg, frames[3 + k])), (fov_deg, oh, ow, k)
 
 
 def _mid_size_geometries():
