@@ -299,8 +299,16 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) v[q][k] = __vadd4(v[q][k], g[q][k]);
                     } else {
+                        // blend band: the guarded fixed-point blend of pb_tiled.cuh where the row's weights
+                        // qualify, the float64 expression otherwise
+                        unsigned ia, ib;
+                        if (fix_weights(r23[q].x, r23[q].y, ia, ib)) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) v[q][k] = blend_px_weighted(v[q][k], r23[q].x, g[q][k], r23[q].y);
+                            for (int k = 0; k < 4; ++k) v[q][k] = blend_px_fix(v[q][k], ia, r23[q].x, g[q][k], ib, r23[q].y);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) v[q][k] = blend_px_weighted(v[q][k], r23[q].x, g[q][k], r23[q].y);
+                        }
                     }
                 }
             }

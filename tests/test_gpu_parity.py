@@ -340,6 +340,9 @@ def test_double_source_batches_blend_band(torch_cuda, fov_deg, monkeypatch):
             assert np.array_equal(out[k], want[k]), (fov_deg, env, k, mismatch_report(out[k], want[k]))
         for k in env:
             monkeypatch.delenv(k)
+    # one frame per call: the single-frame kernel (csrc/pb_sep1.cuh) has the same blend
+    for k in (0, 3, 5):
+        assert np.array_equal(helpers.product_remap(og, (), sg, frames[k]), want[k]), (fov_deg, "single", k)
     # few tiles: a class of tiles may be empty (one tile; a band that sees both lenses everywhere)
     for oh, ow in ((64, 32), (48, 80), (130, 96), (64, 704)):
         og2 = {"kind": "equirect", "height": oh, "width": ow}
