@@ -557,7 +557,7 @@ static bool class_split_off() { return env_int("PB_CLASS_SPLIT", 1) == 0; }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // persistent single-frame kernel: as many CTAs as the device holds at once
-template <int SRC_KIND, int NB>
+template <int SRC_KIND, int NB, int CLS = 0>
 static cudaError_t launch_sep1_one(const TiledArgs& a, cudaStream_t st) {
     const int smem = sep1_smem_bytes(a.sep1_cap, SRC_KIND == PB_KIND_DOUBLE, NB);
     static int max_smem_set[kMaxDevices] = {0};  // per device: the attribute belongs to the function on one device
@@ -565,22 +565,23 @@ static cudaError_t launch_sep1_one(const TiledArgs& a, cudaStream_t st) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= kMaxDevices || smem > max_smem_set[dev]) {
-        e = cudaFuncSetAttribute(remap_sep1_kernel<SRC_KIND, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        e = cudaFuncSetAttribute(remap_sep1_kernel<SRC_KIND, NB, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < kMaxDevices) max_smem_set[dev] = smem;
     }
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, remap_sep1_kernel<SRC_KIND, NB>, kTileThreads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, remap_sep1_kernel<SRC_KIND, NB, CLS>, kTileThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     int grid = sms * per_sm;
     if (const char* env = std::getenv("PB_SEP1_WAVES")) grid *= std::atoi(env);  // tuning experiments
     if (const char* env = std::getenv("PB_SEP1_GRID")) grid = std::atoi(env);
-    const int n_tiles = a.tiles_x * a.tiles_y;
+    const int n_tiles = a.tile_list ? a.n_list : a.tiles_x * a.tiles_y;
+    if (n_tiles <= 0) return cudaSuccess;
     if (grid > n_tiles) grid = n_tiles;
     if (grid < 1) grid = 1;
-    remap_sep1_kernel<SRC_KIND, NB><<<grid, kTileThreads, smem, st>>>(a);
+    remap_sep1_kernel<SRC_KIND, NB, CLS><<<grid, kTileThreads, smem, st>>>(a);
     PB_COUNT_LAUNCH();
     return cudaGetLastError();
 }
@@ -606,6 +607,8 @@ struct pb_plan {
     // (both lenses, blend band, nothing visible); batches run them as two launches (remap_tiled_kernel CLS)
     int* tile_lists;
     int n_one, n_rest;
+    int4* sep1_cls;      // single-frame kernel: descriptor tables of the two classes ([n_one] then [n_rest][2])
+    int sep1_cap_one;    // ... and the stage-buffer capacity of the one-lens class
     int device;
 };
 
@@ -642,6 +645,8 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     p.tables = nullptr;
     p.tile_lists = nullptr;
     p.n_one = p.n_rest = 0;
+    p.sep1_cls = nullptr;
+    p.sep1_cap_one = 24 * 1024;
     p.device = -1;
 }
 
@@ -755,6 +760,37 @@ static void classify_tiles(pb_plan& p, const int4* fp, cudaStream_t st) {
     p.tile_lists = lists;
     p.n_rest = (int)rest.size();
     p.n_one = n_tiles - p.n_rest;
+    // single-frame kernel: per-class descriptor tables, and a buffer size that holds the one
+    // rectangle of (all but 0.5 % of) the one-lens tiles
+    int4* cls = nullptr;
+    if (cudaMalloc((void**)&cls, sizeof(int4) * ((size_t)p.n_one + 2 * (size_t)p.n_rest + 1)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;
+    }
+    if (p.n_one > 0)
+        pb_sep1_table_kernel<<<(p.n_one + 255) / 256, 256, 0, st>>>(footprint_table(p, p.tables), cls, tx, ty, p.raster_band,
+                                                                   2, lists, p.n_one, 1);
+    if (p.n_rest > 0)
+        pb_sep1_table_kernel<<<(p.n_rest + 255) / 256, 256, 0, st>>>(footprint_table(p, p.tables), cls + p.n_one, tx, ty,
+                                                                    p.raster_band, 2, lists + p.n_one, p.n_rest, 0);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaFree(cls);
+        return;
+    }
+    std::vector<int> kib;
+    for (int i = 0; i < p.n_one; ++i) {
+        const int t = one[i];
+        const int4& f = fp[2 * t].z > 0 ? fp[2 * t] : fp[2 * t + 1];
+        const int units = stage_units(f.w >> 1);
+        kib.push_back(units <= kMaxStageUnits ? (f.z * kBoxRows * 16 * units + 1023) >> 10 : 1 << 20);
+    }
+    if (!kib.empty()) {
+        std::sort(kib.begin(), kib.end());
+        int k = kib[kib.size() - 1 - kib.size() / 200];
+        p.sep1_cap_one = std::min(std::max(k, 4), 96) * 1024;
+    }
+    p.sep1_cls = cls;
 }
 
 static void tune_stage(pb_plan& p, cudaStream_t st) {
@@ -993,6 +1029,22 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
                     e = (nb_env == 3 && sep1_smem_bytes(a.sep1_cap, false, 3) <= kMaxTiledSmem)
                             ? launch_sep1_one<PB_KIND_CAMERA, 3>(a, st)
                             : launch_sep1_one<PB_KIND_CAMERA, 2>(a, st);
+                else if (p.sep1_cls && tables == p.tables && !class_split_off()) {
+                    // two grids by tile class, as for batches: the tiles that see both lenses (or the
+                    // blend band) keep the two-rectangle buffers, those that see one lens run as a
+                    // one-slot kernel with small buffers at four CTAs per SM
+                    a.tile_list = p.tile_lists + p.n_one;
+                    a.n_list = p.n_rest;
+                    a.sep1_tab = p.sep1_cls + p.n_one;
+                    e = launch_sep1_one<PB_KIND_DOUBLE, 2, 2>(a, st);
+                    if (e == cudaSuccess) {
+                        a.tile_list = p.tile_lists;
+                        a.n_list = p.n_one;
+                        a.sep1_tab = p.sep1_cls;
+                        a.sep1_cap = env_int("PB_SEP1_ONE_KIB", p.sep1_cap_one >> 10) * 1024;
+                        e = launch_sep1_one<PB_KIND_DOUBLE, 2, 1>(a, st);
+                    }
+                }
                 else
                     e = launch_sep1_one<PB_KIND_DOUBLE, 2>(a, st);
             }
@@ -1135,6 +1187,7 @@ void pb_plan_destroy(pb_plan* plan) {
     if (!plan) return;
     if (plan->tables) cudaFree(plan->tables);
     if (plan->tile_lists) cudaFree(plan->tile_lists);
+    if (plan->sep1_cls) cudaFree(plan->sep1_cls);
     delete plan;
 }
 

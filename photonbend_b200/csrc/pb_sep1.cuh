@@ -27,12 +27,19 @@ namespace pb {
 //   y: first staged byte of a source row (multiple of 16)
 //   z: tile_x | tile_y << 16
 //   w: by0 * pitch + xb0  (byte offset of the rectangle's origin in "staged pitch" coordinates)
+// With a tile list (a class of tiles of a double-fisheye source, pb_plan): entry u describes tile
+// list[u]; one_lens: ONE descriptor per tile, that of the lens the tile sees, bit 31 of x = right lens.
 __global__ void __launch_bounds__(256) pb_sep1_table_kernel(const int4* __restrict__ tile_fp, int4* __restrict__ tab,
-                                                            int tiles_x, int tiles_y, int raster_band, int nslot) {
+                                                            int tiles_x, int tiles_y, int raster_band, int nslot,
+                                                            const int* __restrict__ list = nullptr, int n_list = 0,
+                                                            int one_lens = 0) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= tiles_x * tiles_y) return;
+    if (u >= (list ? n_list : tiles_x * tiles_y)) return;
     int tile_x, tile_y;
-    if (raster_band > 0) {
+    if (list) {
+        tile_y = list[u] / tiles_x;
+        tile_x = list[u] - tile_y * tiles_x;
+    } else if (raster_band > 0) {
         const int per_band = raster_band * tiles_x;
         const int band = u / per_band, within = u - band * per_band;
         const int bh = min(raster_band, tiles_y - band * raster_band);
@@ -53,7 +60,8 @@ __global__ void __launch_bounds__(256) pb_sep1_table_kernel(const int4* __restri
             d.y = fp.y;
             d.w = fp.x * 16 * units + fp.y;
         }
-        tab[u * nslot + s] = d;
+        if (!one_lens) tab[u * nslot + s] = d;
+        else if (fp.z > 0) tab[u] = make_int4(d.x | (s ? (int)0x80000000u : 0), d.y, d.z, d.w);
     }
 }
 
@@ -111,12 +119,16 @@ struct Sep1Slot {
 #endif
 // NB: stage buffers = depth of the load pipeline (tile n is gathered while the loads of tiles
 // n+1 .. n+NB-1 are in flight and those of tile n+NB are issued)
-template <int SRC_KIND, int NB>
-__global__ void __launch_bounds__(kTileThreads, (SRC_KIND == PB_KIND_DOUBLE) ? 3 : PB_SEP1_CAM_CTAS)
+// CLS (double-fisheye source; the plan sorts the tiles into two launches like the batched kernel):
+// 0 = every tile, 1 = the tiles that see exactly one lens at unit weights (one slot, chosen per
+// tile; small buffers, 4 CTAs per SM), 2 = the rest (the code of class 0 over a tile list)
+template <int SRC_KIND, int NB, int CLS = 0>
+__global__ void __launch_bounds__(kTileThreads, (SRC_KIND == PB_KIND_DOUBLE && CLS != 1) ? 3 : PB_SEP1_CAM_CTAS)
 remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
     static_assert(NB >= 2 && NB <= 4, "2..4 stage buffers");
     constexpr bool DBL = (SRC_KIND == PB_KIND_DOUBLE);
-    constexpr int NSLOT = DBL ? 2 : 1;
+    constexpr bool ONE = DBL && CLS == 1;
+    constexpr int NSLOT = (DBL && !ONE) ? 2 : 1;
 
     extern __shared__ __align__(128) unsigned char smem[];
     // [ out tile 0 ][ out tile 1 ][ NB stage buffers ][ ring of 8 tile descriptors ][ NB mbarriers ]
@@ -135,7 +147,7 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
     const int qc = tid & (kQuadsPerRow - 1);
     const int rg = tid >> 3;
     const int G = gridDim.x;
-    const int n_tiles = a.tiles_x * a.tiles_y;
+    const int n_tiles = a.tile_list ? a.n_list : a.tiles_x * a.tiles_y;  // (a list: sep1_tab is that class's table)
     const int4* __restrict__ tab = a.sep1_tab;
 
     if (tid == 0) {
@@ -156,7 +168,7 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
     auto issue = [&](int r, int b) {
         Sep1Slot s0, s1;
         s0.decode(ring[r * 2]);
-        s1.decode(DBL ? ring[r * 2 + 1] : make_int4(0, 0, 0, 0));
+        s1.decode(NSLOT == 2 ? ring[r * 2 + 1] : make_int4(0, 0, 0, 0));
         const int tx = s0.tile & 0xffff, ty = s0.tile >> 16;
         int total = s0.rect + s1.rect;
         if (total > cap) total = 0;  // gathered from global memory: only the table slices are staged
@@ -172,7 +184,7 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
             for (int k = 0; k < s0.nbox; ++k)
                 ptx::tma_load_3d_hint(base + k * kBoxRows * s0.pitch, map, s0.xb0 >> 1, s0.by0 + k * kBoxRows, 0, &bars[b], keep);
         }
-        if (DBL && s1.nbox > 0) {
+        if (NSLOT == 2 && s1.nbox > 0) {
             const CUtensorMap* map = &a.src_maps[(s1.pitch >> 5) - (kMinStageUnits >> 1)];
             for (int k = 0; k < s1.nbox; ++k)
                 ptx::tma_load_3d_hint(base + s0.rect + k * kBoxRows * s1.pitch, map, s1.xb0 >> 1, s1.by0 + k * kBoxRows, 0,
@@ -195,7 +207,8 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
     for (int u = blockIdx.x; u < n_tiles; u += G, ++it, b = (b + 1 == NB) ? 0 : b + 1) {
         const int ob = it & 1;  // output tile
         const int4 d0 = ring[(it & 7) * 2];
-        const int4 d1 = DBL ? ring[(it & 7) * 2 + 1] : make_int4(0, 0, 0, 0);
+        const int4 d1 = NSLOT == 2 ? ring[(it & 7) * 2 + 1] : make_int4(0, 0, 0, 0);
+        const bool right_lens = ONE && d0.x < 0;  // ONE: the lens this tile sees
         // the descriptor of the tile NB + 1 ahead travels while this tile is processed
         int4 pre = make_int4(0, 0, 0, 0);
         if (tid < NSLOT && u + (NB + 1) * G < n_tiles) pre = __ldg(tab + (u + (NB + 1) * G) * NSLOT + tid);
@@ -221,7 +234,11 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
 #pragma unroll
         for (int q = 0; q < kRowsPerThread; ++q) {
             const int r = rg + q * kRowGroups;
-            if (DBL) {
+            if (ONE) {
+                r01[q].x = reinterpret_cast<const double*>(head + kColBytes)[4 * r + (right_lens ? 1 : 0)];
+                r01[q].y = 0.0;
+                r23[q] = make_double2(1.0, 1.0);
+            } else if (DBL) {
                 r01[q] = reinterpret_cast<const double2*>(head + kColBytes)[2 * r];
                 r23[q] = reinterpret_cast<const double2*>(head + kColBytes)[2 * r + 1];
             } else {
@@ -236,8 +253,9 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
 #pragma unroll
         for (int s = 0; s < NSLOT; ++s) {
             const Sep1Slot& S = sl[s];
-            const int w = DBL ? (s ? a.src.wr : a.src.wl) : a.src.W;
-            const double cx = DBL ? (s ? a.src.cxr : a.src.cxl) : a.src.cx;
+            const bool right = ONE ? right_lens : (s != 0);  // right half of a double image: mirrored columns
+            const int w = DBL ? (right ? a.src.wr : a.src.wl) : a.src.W;
+            const double cx = DBL ? (right ? a.src.cxr : a.src.cxl) : a.src.cx;
             unsigned g[kRowsPerThread][4];
             if (S.nbox == 0) {  // block-uniform: nothing of this lens is visible from the tile
 #pragma unroll
@@ -255,9 +273,9 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
                             double fx, fy;
                             camera_fxy(cs[k].x, cs[k].y, s ? r01[q].y : r01[q].x, cy, cx, fx, fy);
                             int px = trunc_abs(fx);
-                            if (s) px = a.src.W - 1 - px;
+                            if (right) px = a.src.W - 1 - px;
                             const int off = trunc_abs(fy) * S.pitch + (px * 3 + base);
-                            g[q][k] = sep1_pick<!DBL>(stage_sa, off);
+                            g[q][k] = sep1_pick<!DBL || ONE>(stage_sa, off);
                         }
                 } else {
 #pragma unroll
@@ -267,10 +285,10 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
                             double fx, fy;
                             camera_fxy(cs[k].x, cs[k].y, s ? r01[q].y : r01[q].x, cy, cx, fx, fy);
                             int px = trunc_abs(fx);
-                            if (s) px = a.src.W - 1 - px;
+                            if (right) px = a.src.W - 1 - px;
                             int off = trunc_abs(fy) * S.pitch + (px * 3 + base);
                             off = inside_image(fx, fy, w, a.src.H) ? off : 0;  // 0: the buffer's zero bytes
-                            g[q][k] = sep1_pick<!DBL>(stage_sa, off);
+                            g[q][k] = sep1_pick<!DBL || ONE>(stage_sa, off);
                         }
                 }
             } else {
@@ -282,7 +300,7 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
                         double fx, fy;
                         camera_fxy(cs[k].x, cs[k].y, s ? r01[q].y : r01[q].x, cy, cx, fx, fy);
                         int px = trunc_abs(fx);
-                        if (s) px = a.src.W - 1 - px;
+                        if (right) px = a.src.W - 1 - px;
                         const int py = trunc_abs(fy);
                         g[q][k] = inside_image(fx, fy, w, a.src.H) ? pick_px_global(frame, py * a.src_pitch + px * 3) : 0u;
                     }
