@@ -19,7 +19,8 @@ ncu --set full --clock-control none --import-source on -k regex:remap_tiled -s 4
     python bench.py --workload T $small > $out/ncu_full_${tag}_T.log 2>&1
 python tests/analysis/kbench.py T:1 cfg1:1 cfg4:1 cfg2:1 cfg3:1 T:16 cfg5:16 --tag $tag > $out/kbench_${tag}.log 2>&1
 for w in T cfg4 cfg2 cfg3; do
-  ncu --set full --clock-control none --import-source on -k regex:remap_ -s 4 -c 1 -f -o $out/prof_${tag}_${w}_1frame \
+  n=1; [ $w = cfg4 ] && n=2   # a double-fisheye source is two grids per call (tile classes)
+  ncu --set full --clock-control none --import-source on -k regex:remap_ -s 4 -c $n -f -o $out/prof_${tag}_${w}_1frame \
       python tests/analysis/kbench.py $w:1 --steps 5 > $out/ncu_single_${tag}_$w.log 2>&1
 done
 # summaries are made here (ncu is on the box); only two reports travel back (64 MiB limit on gpurun_out/)
