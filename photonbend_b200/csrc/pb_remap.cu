@@ -609,6 +609,11 @@ struct pb_plan {
     int n_one, n_rest;
     int4* sep1_cls;      // single-frame kernel: descriptor tables of the two classes ([n_one] then [n_rest][2])
     int sep1_cap_one;    // ... and the stage-buffer capacity of the one-lens class
+    // the two grids of a double-fisheye remap are independent (disjoint tiles): the second one is
+    // forked onto a stream of the plan's own and joined back, so that it fills the SMs the first
+    // one's last wave leaves idle
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_join;
     int device;
 };
 
@@ -647,6 +652,8 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     p.n_one = p.n_rest = 0;
     p.sep1_cls = nullptr;
     p.sep1_cap_one = 24 * 1024;
+    p.side = nullptr;
+    p.ev_fork = p.ev_join = nullptr;
     p.device = -1;
 }
 
@@ -791,6 +798,31 @@ static void classify_tiles(pb_plan& p, const int4* fp, cudaStream_t st) {
         p.sep1_cap_one = std::min(std::max(k, 4), 96) * 1024;
     }
     p.sep1_cls = cls;
+    if (cudaStreamCreateWithFlags(&p.side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (p.side) cudaStreamDestroy(p.side);
+        if (p.ev_fork) cudaEventDestroy(p.ev_fork);
+        p.side = nullptr;
+        p.ev_fork = p.ev_join = nullptr;
+    }
+}
+
+// fork: the plan's side stream picks up after everything enqueued on st so far; join: st waits for it
+static cudaStream_t fork_side(const pb_plan& p, cudaStream_t st) {
+    if (!p.side || env_int("PB_CONCURRENT", 1) == 0) return st;
+    if (cudaEventRecord(p.ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(p.side, p.ev_fork, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return st;
+    }
+    return p.side;
+}
+static cudaError_t join_side(const pb_plan& p, cudaStream_t side, cudaStream_t st) {
+    if (side == st) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(p.ev_join, side);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, p.ev_join, 0);
+    return e;
 }
 
 static void tune_stage(pb_plan& p, cudaStream_t st) {
@@ -1036,7 +1068,8 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
                     a.tile_list = p.tile_lists + p.n_one;
                     a.n_list = p.n_rest;
                     a.sep1_tab = p.sep1_cls + p.n_one;
-                    e = launch_sep1_one<PB_KIND_DOUBLE, 2, 2>(a, st);
+                    const cudaStream_t side = fork_side(p, st);
+                    e = launch_sep1_one<PB_KIND_DOUBLE, 2, 2>(a, side);
                     if (e == cudaSuccess) {
                         a.tile_list = p.tile_lists;
                         a.n_list = p.n_one;
@@ -1044,6 +1077,8 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
                         a.sep1_cap = env_int("PB_SEP1_ONE_KIB", p.sep1_cap_one >> 10) * 1024;
                         e = launch_sep1_one<PB_KIND_DOUBLE, 2, 1>(a, st);
                     }
+                    const cudaError_t ej = join_side(p, side, st);  // always: st must not run ahead of the side grid
+                    if (e == cudaSuccess) e = ej;
                 }
                 else
                     e = launch_sep1_one<PB_KIND_DOUBLE, 2>(a, st);
@@ -1057,13 +1092,16 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
                 a.tile_list = p.tile_lists + p.n_one;
                 a.n_list = p.n_rest;
                 a.stage_bytes = env_int("PB_REST_KIB", 50) * 1024;
-                e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 2>(a, st);
+                const cudaStream_t side = fork_side(p, st);
+                e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 2>(a, side);
                 if (e == cudaSuccess) {
                     a.tile_list = p.tile_lists;
                     a.n_list = p.n_one;
                     a.stage_bytes = env_int("PB_ONE_BYTES", 21 * 1024);  // four CTAs per SM
                     e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 1>(a, st);
                 }
+                const cudaError_t ej = join_side(p, side, st);  // always: st must not run ahead of the side grid
+                if (e == cudaSuccess) e = ej;
             }
             else
                 e = launch_tiled(a, sep, st);
@@ -1188,6 +1226,9 @@ void pb_plan_destroy(pb_plan* plan) {
     if (plan->tables) cudaFree(plan->tables);
     if (plan->tile_lists) cudaFree(plan->tile_lists);
     if (plan->sep1_cls) cudaFree(plan->sep1_cls);
+    if (plan->side) cudaStreamDestroy(plan->side);
+    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
     delete plan;
 }
 
