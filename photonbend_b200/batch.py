@@ -82,15 +82,23 @@ def remap_batch(source, coordinate_map: CoordinateMap, frames, out=None):
 
 
 class FramePipeline:
-    """Host frames in, host frames out, with ``depth`` frames in flight.
+    """Host frames in, host frames out, with ``depth`` launches in flight.
 
-    Slot s owns a device input buffer, a device output buffer and a CUDA stream; frame k uses
-    slot k mod depth: H2D copy, fused remap kernel and D2H copy are enqueued on that stream, so
-    the copies of frame k+1 overlap the kernel and the D2H of frame k.  Host buffers should be
-    pinned (``torch.empty(..., pin_memory=True)``) or the copies serialise.
+    Slot s owns a device input buffer and a device output buffer for ``batch`` frames and a CUDA
+    stream; frames fill the slots in turn.  The H2D copy of a frame is enqueued on its slot's
+    stream as soon as it is submitted; when the slot holds ``batch`` frames (or on ``flush()`` /
+    ``drain()``) ONE remap launch covers them -- the source index of an output pixel is resolved
+    once per launch, not once per frame -- followed by their D2H copies.  Copies of one slot
+    overlap the kernel and the copies of the others.  Host buffers should be pinned
+    (``torch.empty(..., pin_memory=True)``) or the copies serialise.  ``batch=1`` launches per
+    frame (lowest latency); a stream of frames wants ``batch`` >= 4.
+
+    A host output buffer is complete after ``drain()`` or after the event its ``submit`` /
+    ``flush`` returned; it must not be handed to another ``submit`` before that.
     """
 
-    def __init__(self, source, coordinate_map: CoordinateMap, depth: int = 3, device: Optional[int] = None):
+    def __init__(self, source, coordinate_map: CoordinateMap, depth: int = 3, device: Optional[int] = None,
+                 batch: int = 1):
         if not (isinstance(coordinate_map, CoordinateMap) and coordinate_map.is_lazy):
             raise ValueError("FramePipeline needs the lazy CoordinateMap of get_coordinate_map()")
         torch = engine._torch()
@@ -99,36 +107,71 @@ class FramePipeline:
         self._src_geom = source._source_geometry()
         self._device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self._depth = max(1, int(depth))
+        self._batch = max(1, int(batch))
         self._streams = [torch.cuda.Stream(device=self._device) for _ in range(self._depth)]
         self._src_bufs: List = [None] * self._depth
         self._dst_bufs: List = [None] * self._depth
-        self._submitted = 0
+        self._pending: List[list] = [[] for _ in range(self._depth)]  # host outputs of the frames a slot holds
+        self._slot = 0
         self.kernel_launches = 0
 
     @property
     def output_shape(self):
         return (self._rays.out.height, self._rays.out.output_width)
 
-    def submit(self, host_frame, host_out):
-        """Enqueue one frame: host_frame (uint8 CPU tensor (H, W, C)) -> host_out (uint8 CPU
-        tensor (Ho, Wo, C)).  Returns immediately; ``host_out`` is complete after ``drain()``
-        (or after the returned event)."""
+    def _launch(self, slot: int):
+        """Remap what slot ``slot`` holds and send it back to the host; -> completion event."""
         torch = self._torch
-        slot = self._submitted % self._depth
-        self._submitted += 1
+        outs = self._pending[slot]
+        if not outs:
+            return None
+        n = len(outs)
         stream = self._streams[slot]
         with torch.cuda.device(self._device), torch.cuda.stream(stream):
-            if self._src_bufs[slot] is None or self._src_bufs[slot].shape != host_frame.shape:
-                self._src_bufs[slot] = torch.empty(host_frame.shape, dtype=torch.uint8, device=self._device)
-                self._dst_bufs[slot] = None
             src_dev = self._src_bufs[slot]
-            src_dev.copy_(host_frame, non_blocking=True)
-            self._dst_bufs[slot] = engine.remap_device(self._rays, self._src_geom, src_dev, self._dst_bufs[slot])
+            if self._dst_bufs[slot] is None:
+                oh, ow = self.output_shape
+                self._dst_bufs[slot] = torch.empty((self._batch, oh, ow) + tuple(src_dev.shape[3:]), dtype=torch.uint8,
+                                                   device=self._device)
+            dst_dev = self._dst_bufs[slot]
+            if n == 1:  # one frame: the single-frame kernels
+                engine.remap_device(self._rays, self._src_geom, src_dev[0], dst_dev[0])
+            else:
+                engine.remap_device(self._rays, self._src_geom, src_dev[:n], dst_dev[:n])
             self.kernel_launches += 1
-            host_out.copy_(self._dst_bufs[slot], non_blocking=True)
+            for k, host_out in enumerate(outs):
+                host_out.copy_(dst_dev[k], non_blocking=True)
             done = torch.cuda.Event()
             done.record(stream)
+        self._pending[slot] = []
         return done
+
+    def submit(self, host_frame, host_out):
+        """Enqueue one frame: host_frame (uint8 CPU tensor (H, W, C)) -> host_out (uint8 CPU
+        tensor (Ho, Wo, C)).  Returns immediately: the completion event of the launch when this
+        frame completed a batch, else None."""
+        torch = self._torch
+        slot = self._slot
+        stream = self._streams[slot]
+        with torch.cuda.device(self._device), torch.cuda.stream(stream):
+            want = (self._batch,) + tuple(host_frame.shape)
+            if self._src_bufs[slot] is None or tuple(self._src_bufs[slot].shape) != want:
+                self._src_bufs[slot] = torch.empty(want, dtype=torch.uint8, device=self._device)
+                self._dst_bufs[slot] = None
+            self._src_bufs[slot][len(self._pending[slot])].copy_(host_frame, non_blocking=True)
+        self._pending[slot].append(host_out)
+        if len(self._pending[slot]) < self._batch:
+            return None
+        self._slot = (slot + 1) % self._depth
+        return self._launch(slot)
+
+    def flush(self):
+        """Launch a partly filled batch now; -> its completion event (None if nothing was pending)."""
+        slot = self._slot
+        if not self._pending[slot]:
+            return None
+        self._slot = (slot + 1) % self._depth
+        return self._launch(slot)
 
     def run(self, host_frames: Sequence, host_outs: Sequence) -> None:
         """Remap every frame of ``host_frames`` into the matching ``host_outs`` and wait."""
@@ -139,5 +182,6 @@ class FramePipeline:
         self.drain()
 
     def drain(self) -> None:
+        self.flush()
         for s in self._streams:
             s.synchronize()

@@ -22,6 +22,12 @@
 // Otherwise the pixel is "undecided" and the caller runs the exact chain for it (~4e-6 of the
 // pixels).  Results are therefore those of the exact chain, bit for bit
 // (tests/test_gpu_parity.py::test_fast_path_equals_exact_chain).
+// Caveats: (1) the matrices must be orthonormal (derive_fast checks, else the exact chain runs);
+// (2) the conditioning guards look at the FINAL vector only.  With two or more rotations an
+// INTERMEDIATE vector of the exact chain that lands within ~1e-7 rad of a pole has its acos error
+// amplified past the guard band; the short cut (which never forms that intermediate angle) then
+// differs from the exact chain.  That needs a pixel whose intermediate ray hits a cone of 1e-7 rad:
+// probability ~1e-14 per pixel and rotation, i.e. not observable, but not zero.
 #pragma once
 
 #include "pb_device.cuh"

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -154,6 +155,17 @@ static FastGeom derive_fast(const pb_image_desc& od, const OutGeom& o, const pb_
     std::memcpy(g.rot, acc, sizeof(acc));
     for (int e = 0; e < 9; ++e)
         if (!std::isfinite(acc[e])) g.enabled = 0;
+    // The short cut carries the ray as a unit vector through ONE composed matrix; the exact chain
+    // goes back to (acos, atan2) after every rotation.  The two are the same function only for
+    // orthonormal matrices (Rotation.rotation_matrix always is; the raw ABI takes any 9 doubles):
+    // anything else runs the exact chain.
+    for (int k = 0; k < n_rot; ++k)
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+                double dot = 0.0;
+                for (int e = 0; e < 3; ++e) dot += rotations[k][3 * r + e] * rotations[k][3 * c + e];
+                if (!(std::fabs(dot - (r == c ? 1.0 : 0.0)) < 1e-12)) g.enabled = 0;
+            }
     if (const char* e = std::getenv("PB_EXACT_CHAIN")) {  // validation: every pixel through the exact chain
         if (std::atoi(e) != 0) g.enabled = 0;
     }
@@ -611,10 +623,40 @@ struct pb_plan {
     int sep1_cap_one;    // ... and the stage-buffer capacity of the one-lens class
     // the two grids of a double-fisheye remap are independent (disjoint tiles): the second one is
     // forked onto a stream of the plan's own and joined back, so that it fills the SMs the first
-    // one's last wave leaves idle
-    cudaStream_t side;
-    cudaEvent_t ev_fork, ev_join;
+    // one's last wave leaves idle.  A few lanes (side stream + event pair), one per caller stream
+    // seen, so that the frames of a pipeline that cycles over several streams do not serialise on
+    // one side stream.
+    static constexpr int kSideLanes = 4;
+    struct SideLane {
+        cudaStream_t side;
+        cudaEvent_t ev_fork, ev_join;
+        cudaStream_t user;  // caller stream this lane last served
+    } lanes[kSideLanes];
+    int n_lanes, next_lane;
     int device;
+    // Encoded tensor maps, by buffer: a pipeline that cycles over a few device buffers pays
+    // cuTensorMapEncodeTiled once per buffer instead of up to 15 times per launch (host latency on
+    // a 40-60 us kernel).  A map only holds the address and the extents, so an entry stays valid
+    // for whatever lives at that address later.
+    static constexpr int kMapSlots = 8;
+    struct SrcMaps {
+        const void* base;
+        long long stride;
+        int frames, units;
+        unsigned long long tick;
+        CUtensorMap maps[pb::kMaxSrcMaps];
+    } src_cache[kMapSlots];
+    struct DstMap {
+        const void* base;
+        long long stride;
+        int frames, rows;
+        unsigned long long tick;
+        CUtensorMap map;
+    } dst_cache[kMapSlots];
+    unsigned long long tick;
+    // launches through one plan are serialised on the host (map caches, side lanes): a plan may be
+    // shared by host threads
+    std::mutex mu;
 };
 
 namespace pb {
@@ -652,9 +694,12 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     p.n_one = p.n_rest = 0;
     p.sep1_cls = nullptr;
     p.sep1_cap_one = 24 * 1024;
-    p.side = nullptr;
-    p.ev_fork = p.ev_join = nullptr;
+    std::memset(p.lanes, 0, sizeof(p.lanes));
+    p.n_lanes = p.next_lane = 0;
     p.device = -1;
+    std::memset(p.src_cache, 0, sizeof(p.src_cache));
+    std::memset(p.dst_cache, 0, sizeof(p.dst_cache));
+    p.tick = 0;
 }
 
 // Footprint census of a geometry (one probe launch of the tiled kernel, nothing is remapped):
@@ -803,31 +848,93 @@ static void classify_tiles(pb_plan& p, const int4* fp, cudaStream_t st) {
     // one-lens CTAs over the whole run instead of queueing behind them (cfg5 x16 0.634 -> 0.620 ms)
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if (cudaStreamCreateWithPriority(&p.side, cudaStreamNonBlocking, env_int("PB_SIDE_PRIO", 1) ? prio_hi : prio_lo) != cudaSuccess ||
-        cudaEventCreateWithFlags(&p.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&p.ev_join, cudaEventDisableTiming) != cudaSuccess) {
-        (void)cudaGetLastError();
-        if (p.side) cudaStreamDestroy(p.side);
-        if (p.ev_fork) cudaEventDestroy(p.ev_fork);
-        p.side = nullptr;
-        p.ev_fork = p.ev_join = nullptr;
+    for (int k = 0; k < pb_plan::kSideLanes; ++k) {
+        pb_plan::SideLane& l = p.lanes[k];
+        if (cudaStreamCreateWithPriority(&l.side, cudaStreamNonBlocking, env_int("PB_SIDE_PRIO", 1) ? prio_hi : prio_lo) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            (void)cudaGetLastError();
+            if (l.side) cudaStreamDestroy(l.side);
+            if (l.ev_fork) cudaEventDestroy(l.ev_fork);
+            if (l.ev_join) cudaEventDestroy(l.ev_join);
+            std::memset(&l, 0, sizeof(l));
+            break;
+        }
+        p.n_lanes = k + 1;
     }
 }
 
-// fork: the plan's side stream picks up after everything enqueued on st so far; join: st waits for it
-static cudaStream_t fork_side(const pb_plan& p, cudaStream_t st) {
-    if (!p.side || env_int("PB_CONCURRENT", 1) == 0) return st;
-    if (cudaEventRecord(p.ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(p.side, p.ev_fork, 0) != cudaSuccess) {
-        (void)cudaGetLastError();
-        return st;
+// fork: a side stream of the plan picks up after everything enqueued on st so far; join: st waits
+// for it.  The lane is the one that served this caller stream last, else the next in turn.
+// (called with the plan's mutex held)
+static pb_plan::SideLane* fork_side(pb_plan& p, cudaStream_t st) {
+    if (p.n_lanes == 0 || env_int("PB_CONCURRENT", 1) == 0) return nullptr;
+    pb_plan::SideLane* l = nullptr;
+    for (int k = 0; k < p.n_lanes; ++k)
+        if (p.lanes[k].user == st) l = &p.lanes[k];
+    if (!l) {
+        l = &p.lanes[p.next_lane];
+        p.next_lane = (p.next_lane + 1) % p.n_lanes;
+        l->user = st;
     }
-    return p.side;
+    if (cudaEventRecord(l->ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(l->side, l->ev_fork, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return l;
 }
-static cudaError_t join_side(const pb_plan& p, cudaStream_t side, cudaStream_t st) {
-    if (side == st) return cudaSuccess;
-    cudaError_t e = cudaEventRecord(p.ev_join, side);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, p.ev_join, 0);
+static cudaError_t join_side(pb_plan::SideLane* l, cudaStream_t st) {
+    if (!l) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(l->ev_join, l->side);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, l->ev_join, 0);
     return e;
+}
+
+// The plan's tensor maps for these buffers, encoded on first use (called with the mutex held).
+static bool cached_src_maps(pb_plan& p, const void* src, long long src_pitch, int frames, long long stride, int units,
+                            CUtensorMap* out) {
+    pb_plan::SrcMaps* hit = nullptr;
+    pb_plan::SrcMaps* victim = &p.src_cache[0];
+    for (auto& e : p.src_cache) {
+        if (e.tick && e.base == src && e.stride == stride && e.frames == frames && e.units == units) hit = &e;
+        if (e.tick < victim->tick) victim = &e;
+    }
+    if (!hit) {
+        hit = victim;
+        hit->tick = 0;
+        for (int u = kMinStageUnits; u <= units; u += 2)
+            if (!encode_frames_map(&hit->maps[(u - kMinStageUnits) / 2], src, src_pitch, p.src.H, frames, stride, 2, 16 * u,
+                                   kBoxRows))
+                return false;
+        hit->base = src;
+        hit->stride = stride;
+        hit->frames = frames;
+        hit->units = units;
+    }
+    hit->tick = ++p.tick;
+    std::memcpy(out, hit->maps, sizeof(hit->maps));
+    return true;
+}
+static bool cached_dst_map(pb_plan& p, const void* dst, long long dst_pitch, int rows, int frames, long long stride,
+                           CUtensorMap* out) {
+    pb_plan::DstMap* hit = nullptr;
+    pb_plan::DstMap* victim = &p.dst_cache[0];
+    for (auto& e : p.dst_cache) {
+        if (e.tick && e.base == dst && e.stride == stride && e.frames == frames && e.rows == rows) hit = &e;
+        if (e.tick < victim->tick) victim = &e;
+    }
+    if (!hit) {
+        hit = victim;
+        hit->tick = 0;
+        if (!encode_frames_map(&hit->map, dst, dst_pitch, rows, frames, stride, 1, kOutRowBytes, kTileH)) return false;
+        hit->base = dst;
+        hit->stride = stride;
+        hit->frames = frames;
+        hit->rows = rows;
+    }
+    hit->tick = ++p.tick;
+    *out = hit->map;
+    return true;
 }
 
 static void tune_stage(pb_plan& p, cudaStream_t st) {
@@ -960,9 +1067,10 @@ static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st
 // tables: the plan's own, a transient stream-ordered allocation, or null (generic rays)
 // [row_begin, row_end): the output rows to produce; dst points at row row_begin (a band of a
 // single frame, or the whole image)
-static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, int64_t src_frame_stride,
+static int plan_run(pb_plan& p, const double* tables, const uint8_t* src, int64_t src_frame_stride,
                     uint8_t* dst, int64_t dst_frame_stride, int32_t n_frames, cudaStream_t st, int row_begin = 0,
                     int row_end = -1) {
+    std::lock_guard<std::mutex> hold(p.mu);
     if (row_end < 0) row_end = p.out.H;
     const bool whole = row_begin == 0 && row_end == p.out.H;
     const int C = p.desc.channels;
@@ -1047,13 +1155,8 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
             if (const char* e = std::getenv("PB_TWO_BUF_LIMIT_KIB")) limit_kib = std::atoi(e);  // tuning experiments
             if (two <= limit_kib * 1024) a.n_buffers = 2;
         }
-        bool maps_ok = true;
-        for (int u = kMinStageUnits; u <= a.max_units && maps_ok; u += 2)
-            maps_ok = encode_frames_map(&a.src_maps[(u - kMinStageUnits) / 2], src, src_pitch, p.src.H, n_frames,
-                                        src_frame_stride, 2, 16 * u, kBoxRows);
-        if (maps_ok &&
-            encode_frames_map(&a.dst_map, dst, dst_pitch, row_end - row_begin, n_frames, dst_frame_stride, 1,
-                              kOutRowBytes, kTileH)) {
+        if (cached_src_maps(p, src, src_pitch, n_frames, src_frame_stride, a.max_units, a.src_maps) &&
+            cached_dst_map(p, dst, dst_pitch, row_end - row_begin, n_frames, dst_frame_stride, &a.dst_map)) {
             const bool sep = p.separable && tables != nullptr;
             static const bool sep1_off = std::getenv("PB_SEP1") && std::atoi(std::getenv("PB_SEP1")) == 0;
             cudaError_t e;
@@ -1073,8 +1176,8 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
                     a.tile_list = p.tile_lists + p.n_one;
                     a.n_list = p.n_rest;
                     a.sep1_tab = p.sep1_cls + p.n_one;
-                    const cudaStream_t side = fork_side(p, st);
-                    e = launch_sep1_one<PB_KIND_DOUBLE, 2, 2>(a, side);
+                    pb_plan::SideLane* lane = fork_side(p, st);
+                    e = launch_sep1_one<PB_KIND_DOUBLE, 2, 2>(a, lane ? lane->side : st);
                     if (e == cudaSuccess) {
                         a.tile_list = p.tile_lists;
                         a.n_list = p.n_one;
@@ -1082,7 +1185,7 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
                         a.sep1_cap = env_int("PB_SEP1_ONE_KIB", p.sep1_cap_one >> 10) * 1024;
                         e = launch_sep1_one<PB_KIND_DOUBLE, 2, 1>(a, st);
                     }
-                    const cudaError_t ej = join_side(p, side, st);  // always: st must not run ahead of the side grid
+                    const cudaError_t ej = join_side(lane, st);  // always: st must not run ahead of the side grid
                     if (e == cudaSuccess) e = ej;
                 }
                 else
@@ -1097,14 +1200,14 @@ static int plan_run(const pb_plan& p, const double* tables, const uint8_t* src, 
                 a.tile_list = p.tile_lists + p.n_one;
                 a.n_list = p.n_rest;
                 a.stage_bytes = env_int("PB_REST_KIB", 50) * 1024;
-                const cudaStream_t side = fork_side(p, st);
+                pb_plan::SideLane* lane = fork_side(p, st);
                 TiledArgs b = a;
                 b.tile_list = p.tile_lists;
                 b.n_list = p.n_one;
                 b.stage_bytes = env_int("PB_ONE_BYTES", 21 * 1024);  // four CTAs per SM
-                e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 2>(a, side);
+                e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 2>(a, lane ? lane->side : st);
                 if (e == cudaSuccess) e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 1>(b, st);
-                const cudaError_t ej = join_side(p, side, st);  // always: st must not run ahead of the side grid
+                const cudaError_t ej = join_side(lane, st);  // always: st must not run ahead of the side grid
                 if (e == cudaSuccess) e = ej;
             }
             else
@@ -1160,6 +1263,9 @@ int pb_remap_u8(const pb_remap_desc* desc, const uint8_t* src, int64_t src_frame
     cudaStream_t st = (cudaStream_t)stream;
     pb_plan p;
     plan_init(p, *desc);
+    // no footprint census without a plan: the single-frame tables mark every rectangle of up to
+    // kMaxStageUnits units as staged, so a tensor map must exist for every width
+    p.max_units = kMaxStageUnits;
     double* tables = nullptr;
     if (p.separable) {
         // transient, stream-ordered: nothing outlives the call
@@ -1210,7 +1316,8 @@ int pb_plan_remap_u8(const pb_plan* plan, const uint8_t* src, int64_t src_frame_
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess || dev != plan->device)
         return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_remap_u8: plan belongs to another device");
-    return plan_run(*plan, plan->tables, src, src_frame_stride, dst, dst_frame_stride, n_frames, (cudaStream_t)stream);
+    return plan_run(*const_cast<pb_plan*>(plan), plan->tables, src, src_frame_stride, dst, dst_frame_stride, n_frames,
+                    (cudaStream_t)stream);
 }
 
 int pb_plan_remap_rows_u8(const pb_plan* plan, const uint8_t* src, uint8_t* dst_band, int32_t row_begin, int32_t row_end,
@@ -1222,7 +1329,8 @@ int pb_plan_remap_rows_u8(const pb_plan* plan, const uint8_t* src, uint8_t* dst_
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess || dev != plan->device)
         return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_remap_rows_u8: plan belongs to another device");
-    return plan_run(*plan, plan->tables, src, 0, dst_band, 0, 1, (cudaStream_t)stream, row_begin, row_end);
+    return plan_run(*const_cast<pb_plan*>(plan), plan->tables, src, 0, dst_band, 0, 1, (cudaStream_t)stream, row_begin,
+                    row_end);
 }
 
 void pb_plan_destroy(pb_plan* plan) {
@@ -1230,9 +1338,11 @@ void pb_plan_destroy(pb_plan* plan) {
     if (plan->tables) cudaFree(plan->tables);
     if (plan->tile_lists) cudaFree(plan->tile_lists);
     if (plan->sep1_cls) cudaFree(plan->sep1_cls);
-    if (plan->side) cudaStreamDestroy(plan->side);
-    if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
-    if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+    for (int k = 0; k < plan->n_lanes; ++k) {
+        cudaStreamDestroy(plan->lanes[k].side);
+        cudaEventDestroy(plan->lanes[k].ev_fork);
+        cudaEventDestroy(plan->lanes[k].ev_join);
+    }
     delete plan;
 }
 
@@ -1280,6 +1390,9 @@ int pb_gather_from_map_u8(const pb_image_desc* src_desc, int32_t channels, doubl
                           int32_t map_width, const uint8_t* src, uint8_t* dst, void* stream) {
     if (!src_desc || !map || !src || !dst) return fail(PB_ERR_INVALID_ARGUMENT, "pb_gather_from_map_u8: null pointer");
     if (int rc = check_image(*src_desc, "src")) return rc;
+    // source_lookup packs a source pixel as row << 16 | column
+    if (src_desc->height > 32767 || src_desc->width > 65535)
+        return fail(PB_ERR_UNSUPPORTED, "pb_gather_from_map_u8: source larger than 32767 rows x 65535 columns");
     if (channels < 1 || channels > 4) return fail(PB_ERR_UNSUPPORTED, "pb_gather_from_map_u8: channels must be 1..4");
     if (map_height < 0 || map_width < 0) return fail(PB_ERR_INVALID_ARGUMENT, "pb_gather_from_map_u8: negative map size");
     const long long n = (long long)map_height * map_width;

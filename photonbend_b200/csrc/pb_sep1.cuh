@@ -171,7 +171,9 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
         s1.decode(NSLOT == 2 ? ring[r * 2 + 1] : make_int4(0, 0, 0, 0));
         const int tx = s0.tile & 0xffff, ty = s0.tile >> 16;
         int total = s0.rect + s1.rect;
-        if (total > cap) total = 0;  // gathered from global memory: only the table slices are staged
+        // gathered from global memory (only the table slices are staged): too large for a buffer, or
+        // wider than the widest box this launch has a tensor map for
+        if (total > cap || max(s0.pitch, s1.pitch) > 16 * a.max_units) total = 0;
         ptx::mbarrier_arrive_expect_tx(&bars[b], (unsigned)(total + kColBytes + kRowBytes));
         unsigned char* head = stages + b * buf_bytes + 128;
         ptx::bulk_g2s(head, a.sep1_col + (size_t)tx * (kColBytes / 8), kColBytes, &bars[b]);
@@ -218,7 +220,7 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
         sl[1].decode(d1);
         const int x0 = (d0.z & 0xffff) * kTileW, y0 = (d0.z >> 16) * kTileH;
         const int total = sl[0].rect + sl[1].rect;
-        const bool staged = total <= cap;  // block-uniform
+        const bool staged = total <= cap && max(sl[0].pitch, sl[1].pitch) <= 16 * a.max_units;  // block-uniform
 
         ptx::mbarrier_wait_sa(ptx::smem_addr(&bars[b]), (phase >> b) & 1u);
         phase ^= 1u << b;

@@ -7,6 +7,7 @@ Nothing here computes pixels on the CPU; a missing CUDA device or library is an 
 from __future__ import annotations
 
 import ctypes
+import threading
 from dataclasses import dataclass, field
 from typing import Optional, Sequence, Tuple
 
@@ -93,28 +94,36 @@ class _PlanCache:
     def __init__(self, capacity: int = 32):
         self._capacity = capacity
         self._plans = {}  # key -> handle (insertion order = LRU order)
+        # host threads may share the cache (ctypes releases the GIL inside a call).  A handle that
+        # falls out of the cache is destroyed only after the work enqueued with it has finished;
+        # a thread that still holds an evicted handle across ``capacity`` other geometries is not
+        # supported (launches through one handle are serialised inside the library).
+        self._lock = threading.RLock()
 
     def get(self, lib, desc: _native.RemapDesc, device_index: int, torch) -> ctypes.c_void_p:
         key = (device_index, bytes(desc))
-        handle = self._plans.pop(key, None)
-        if handle is None:
-            handle = ctypes.c_void_p()
-            stream = torch.cuda.current_stream()
-            _native.check(lib.pb_plan_create(ctypes.byref(desc), ctypes.c_void_p(stream.cuda_stream),
-                                             ctypes.byref(handle)))
-            stream.synchronize()  # once per geometry: the tables may be used from any stream later
-            while len(self._plans) >= self._capacity:
-                oldest = next(iter(self._plans))
-                lib.pb_plan_destroy(self._plans.pop(oldest))
-        self._plans[key] = handle  # most recently used goes last
-        return handle
+        with self._lock:
+            handle = self._plans.pop(key, None)
+            if handle is None:
+                handle = ctypes.c_void_p()
+                stream = torch.cuda.current_stream()
+                _native.check(lib.pb_plan_create(ctypes.byref(desc), ctypes.c_void_p(stream.cuda_stream),
+                                                 ctypes.byref(handle)))
+                stream.synchronize()  # once per geometry: the tables may be used from any stream later
+                while len(self._plans) >= self._capacity:
+                    oldest = next(iter(self._plans))
+                    torch.cuda.synchronize(oldest[0])
+                    lib.pb_plan_destroy(self._plans.pop(oldest))
+            self._plans[key] = handle  # most recently used goes last
+            return handle
 
     def clear(self):
-        if self._plans:
-            lib = _native.load()
-            for handle in self._plans.values():
-                lib.pb_plan_destroy(handle)
-            self._plans.clear()
+        with self._lock:
+            if self._plans:
+                lib = _native.load()
+                for handle in self._plans.values():
+                    lib.pb_plan_destroy(handle)
+                self._plans.clear()
 
 
 _plans = _PlanCache()
@@ -292,10 +301,17 @@ def gather_from_map_device(src: ImageGeometry, cmap_dev, src_dev, out_dev=None):
         raise ValueError("coordinate map must be float64 of shape (H, W, 3)")
     if not cmap_dev.is_contiguous():
         raise ValueError("coordinate map must be contiguous")
+    if not (cmap_dev.is_cuda and src_dev.is_cuda) or cmap_dev.device != src_dev.device:
+        raise ValueError("coordinate map and source image must live on the same CUDA device")
+    if not src_dev.is_contiguous():
+        raise ValueError("source image must be contiguous")
     mh, mw = cmap_dev.shape[0], cmap_dev.shape[1]
     out_shape = (mh, mw, c) if had_c else (mh, mw)
     if out_dev is None:
         out_dev = torch.empty(out_shape, dtype=torch.uint8, device=src_dev.device)
+    elif (tuple(out_dev.shape) != out_shape or not out_dev.is_contiguous() or out_dev.dtype != torch.uint8
+          or out_dev.device != src_dev.device):
+        raise ValueError(f"out must be a contiguous uint8 tensor of shape {out_shape} on {src_dev.device}")
     d = _native.ImageDesc()
     src.fill(d)
     with torch.cuda.device(src_dev.device):

@@ -22,6 +22,11 @@ pytestmark = pytest.mark.gpu
 
 CASES = case_matrix.all_cases()
 BY_ID = {c[0]: c for c in CASES}
+# Cases in which MORE than 1 % of the reference's own pixels hang on the last ulps of NumPy's libm
+# (helpers.stable_pixel_mask): a property of the geometry, counted with the oracle alone by
+# tests/test_oracle_golden.py::test_degenerate_case_census on the CPU -- the GPU tests may not see more.
+MAX_DEGENERATE_GOLDEN = 62   # of the 585 stored reference outputs
+MAX_DEGENERATE_MATRIX = 83   # of the 1701 cases
 
 
 @pytest.fixture(scope="module")
@@ -73,6 +78,10 @@ def test_small_matrix_against_golden_outputs(torch_cuda, golden_small):
     print(f"golden outputs: {n_bad} differing pixels of {n_px}; {n_degenerate} degenerate cases "
           f"(reference value depends on the last ulps of libm over >1% of the image) checked on their stable pixels only")
     assert n_bad / n_px <= 1e-4, (n_bad, n_px)
+    # "degenerate" is a property of the reference's geometry (360-degree stereographic lenses, a
+    # lat == pi row wrap over a whole row), not of this implementation: the count is pinned so that
+    # a regression cannot hide behind it
+    assert n_degenerate <= MAX_DEGENERATE_GOLDEN, n_degenerate
 
 
 def test_small_matrix_against_numpy_oracle(torch_cuda, golden_small):
@@ -94,6 +103,7 @@ def test_small_matrix_against_numpy_oracle(torch_cuda, golden_small):
     print(f"small matrix: {n_bad} differing pixels of {n_px} in {n_cases_bad} of {len(CASES) - n_degenerate} "
           f"well-conditioned cases; {n_degenerate} degenerate cases checked on their stable pixels only")
     assert n_bad / n_px <= 1e-4, (n_bad, n_px)
+    assert n_degenerate <= MAX_DEGENERATE_MATRIX, n_degenerate
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "T"])
@@ -463,7 +473,9 @@ def test_second_device_in_one_process(torch_cuda):
         rotated = helpers.product_image(sg, batch[0]).process_coordinate_map(helpers.product_map(og, [(0.3, -0.7, 1.1)]))
         assert np.array_equal(out.cpu().numpy()[0], want[0]) and np.array_equal(out.cpu().numpy()[1], want[1]), dev
         assert np.array_equal(single.cpu().numpy(), want[1]), dev
-        assert mismatch_report(rotated.cpu().numpy(), numpy_port.remap(og, [(0.3, -0.7, 1.1)], sg, frames[0]))[2] <= 25, dev
+        # a rotated double-fisheye source: only the 1-LSB blend-truncation class may differ
+        _, max_abs, n_bad = mismatch_report(rotated.cpu().numpy(), numpy_port.remap(og, [(0.3, -0.7, 1.1)], sg, frames[0]))
+        assert n_bad == 0 or (max_abs == 1 and n_bad <= 25), (dev, n_bad, max_abs)
 
 
 @pytest.mark.parametrize("rots", [(), ((0.3, -0.7, 1.1),)], ids=["separable", "rotated"])
@@ -486,3 +498,161 @@ def test_row_bands_equal_the_whole_frame(torch_cuda, rots):
     for rows in (range(0, 1), range(5, 133), range(64, 65), range(419, 420), range(100, 100)):
         band = remap_row_band(source, cmap, frame, rows).cpu().numpy()
         assert np.array_equal(band, whole[rows.start:rows.stop]), (rots, rows)
+
+
+def _cfg5_frames(n):
+    from photonbend_b200 import workloads
+
+    wl = workloads.WORKLOADS["cfg5"]
+    with open(os.path.join(GOLDEN, "cfg5_frames.json")) as fh:
+        golden = json.load(fh)["frames"]
+    frames = []
+    for k in range(n):
+        image = workloads.source_image(wl, frame=k)
+        assert hashlib.sha256(image.tobytes()).hexdigest() == golden[k]["src_sha256"], k
+        frames.append(image)
+    return wl, golden, frames
+
+
+@pytest.mark.parametrize("concurrent", ["1", "0"], ids=["two-grids-concurrent", "two-grids-in-sequence"])
+def test_cfg5_full_size_batch(torch_cuda, monkeypatch, concurrent):
+    """BASELINE config 5 as bench.py runs it: distinct full-size (3840x7680) double-fisheye frames
+    (seeds 1234 + k) through ONE remap_batch call -- the class-split batched kernel, census-picked
+    stage sizes, both grids (on two streams, and in sequence with PB_CONCURRENT=0) -- every frame's
+    sha256 against the live reference's (tests/golden/cfg5_frames.json, made by
+    tests/golden/make_golden_cfg5.py from the unmodified reference, projection.py:408-462)."""
+    torch = torch_cuda
+    from photonbend_b200 import engine
+    from photonbend_b200.batch import remap_batch
+
+    monkeypatch.setenv("PB_CONCURRENT", concurrent)
+    engine.clear_plan_cache()
+    n = 6
+    wl, golden, frames = _cfg5_frames(n)
+    batch = torch.from_numpy(np.stack(frames)).cuda()
+    source = helpers.product_image(wl["src"], batch)
+    cmap = helpers.product_map(wl["out"], wl["rotations"])
+    out = remap_batch(source, cmap, batch)
+    out2 = remap_batch(source, cmap, batch, torch.empty_like(out))  # a second launch into another buffer
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    out = out.cpu().numpy()
+    for k in range(n):
+        got = hashlib.sha256(out[k].tobytes()).hexdigest()
+        if got != golden[k]["out_sha256"]:
+            from oracle import c_port
+
+            want = c_port.remap(wl["out"], wl["rotations"], wl["src"], frames[k])
+            assert hashlib.sha256(want.tobytes()).hexdigest() == golden[k]["out_sha256"], ("oracle vs reference", k)
+            raise AssertionError((concurrent, k, mismatch_report(out[k], want)))
+    engine.clear_plan_cache()
+
+
+@pytest.mark.parametrize("batch", [1, 3], ids=["launch-per-frame", "three-frames-per-launch"])
+def test_frame_pipeline_full_size(torch_cuda, batch):
+    """batch.FramePipeline (the API bench.py's e2e figure is quoted through): depth 3, eight pinned
+    host frames of config 5 in, eight pinned host frames out, per-frame sha256 against the live
+    reference.  Three streams share one plan (tensor-map cache, side-stream lanes); with batch=3
+    the last launch is a partly filled batch (8 = 3 + 3 + 2)."""
+    torch = torch_cuda
+    from photonbend_b200.batch import FramePipeline
+
+    n = 8
+    wl, golden, frames = _cfg5_frames(n)
+    host_in = []
+    for f in frames:
+        t = torch.empty(f.shape, dtype=torch.uint8, pin_memory=True)
+        t.numpy()[...] = f
+        host_in.append(t)
+    oh, ow, _ = workloads_shape(wl)
+    host_out = [torch.zeros((oh, ow, 3), dtype=torch.uint8, pin_memory=True) for _ in range(n)]
+    source = helpers.product_image(wl["src"], frames[0])
+    cmap = helpers.product_map(wl["out"], wl["rotations"])
+    pipe = FramePipeline(source, cmap, depth=3, batch=batch)
+    for rounds in range(2):  # the second round reuses every device buffer and cached tensor map
+        pipe.run(host_in, host_out)
+        for k in range(n):
+            assert hashlib.sha256(host_out[k].numpy().tobytes()).hexdigest() == golden[k]["out_sha256"], (batch, rounds, k)
+            host_out[k].zero_()
+    assert pipe.kernel_launches == 2 * (n if batch == 1 else 3)
+
+
+def workloads_shape(wl):
+    from photonbend_b200 import workloads
+
+    return workloads.output_shape(wl["out"])
+
+
+def test_plan_less_abi_wide_short_footprints(torch_cuda):
+    """pb_remap_u8 WITHOUT a plan (the documented drop-in entry point) on an un-rotated equirect
+    output whose tiles have wide, short source footprints (21..31 sixteen-byte units): every box
+    width needs its tensor map although no census ran (the single-frame kernel
+    indexed maps that were never encoded).  Several tile rows, one frame and a batch."""
+    import ctypes
+
+    torch = torch_cuda
+    from oracle import numpy_port
+    from photonbend_b200 import _native
+
+    lib = _native.load()
+    for (sh, sw, oh, ow, lens, fov) in ((2048, 2048, 2048, 1024, "equidistant", 360), (1024, 1024, 640, 256, "equisolid", 300),
+                                        (1536, 1536, 1024, 512, "stereographic", 200)):
+        sg = {"kind": "camera", "height": sh, "width": sw, "lens": lens, "fov": case_matrix.rad(fov),
+              "magnitude": sw / 2 - 0.5}
+        og = {"kind": "equirect", "height": oh, "width": ow}
+        d = _native.RemapDesc()
+        d.out.kind, d.out.height, d.out.width = _native.KIND_EQUIRECT, oh, ow
+        d.src.kind, d.src.height, d.src.width = _native.KIND_CAMERA, sh, sw
+        d.src.lens = numpy_port.LENS_NAMES.index(lens)
+        d.src.fov = sg["fov"]
+        d.src.f_distance = numpy_port.focal_distance(sg)
+        d.channels, d.n_rotations = 3, 0
+        images = np.stack([case_matrix.case_image(sg, 40 + k) for k in range(2)])
+        src = torch.from_numpy(images).cuda()
+        for n_frames in (1, 2):
+            dst = torch.zeros((n_frames, oh, ow, 3), dtype=torch.uint8, device="cuda")
+            rc = lib.pb_remap_u8(ctypes.byref(d), src.data_ptr(), sh * sw * 3, dst.data_ptr(), oh * ow * 3, n_frames,
+                                 torch.cuda.current_stream().cuda_stream)
+            assert rc == 0, lib.pb_last_error()
+            torch.cuda.synchronize()
+            got = dst.cpu().numpy()
+            for k in range(n_frames):
+                assert np.array_equal(got[k], numpy_port.remap(og, (), sg, images[k])), (lens, n_frames, k)
+
+
+def test_plan_shared_by_host_threads(torch_cuda):
+    """One geometry remapped from four host threads at once, each on its own CUDA stream (ctypes
+    releases the GIL inside the call): launches through one pb_plan are serialised inside the
+    library (tensor-map caches, side-stream lanes), results are those of the oracle."""
+    import threading
+
+    torch = torch_cuda
+    from oracle import numpy_port
+
+    sg = {"kind": "double", "height": 336, "width": 672, "lens": "equidistant", "fov": case_matrix.rad(195)}
+    og = {"kind": "equirect", "height": 352, "width": 704}
+    images = [case_matrix.case_image(sg, 700 + k) for k in range(4)]
+    want = [numpy_port.remap(og, (), sg, im) for im in images]
+    cmap = helpers.product_map(og, ())
+    helpers.product_image(sg, torch.from_numpy(images[0]).cuda()).process_coordinate_map(cmap)  # plan exists
+    errors = []
+
+    def worker(k):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                dev = torch.from_numpy(images[k]).cuda()
+                for _ in range(25):
+                    out = helpers.product_image(sg, dev).process_coordinate_map(cmap)
+                stream.synchronize()
+                if not np.array_equal(out.cpu().numpy(), want[k]):
+                    errors.append(k)
+        except Exception as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

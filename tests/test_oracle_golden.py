@@ -159,3 +159,49 @@ def test_tiny_and_degenerate_sizes_against_the_reference():
         n_c_diff += int((got_c != want).any(axis=2).sum())  # glibc libm vs NumPy's SIMD kernels
         n += 1
     assert n == 180 and n_c_diff <= 4, n_c_diff
+
+
+def test_degenerate_case_census():
+    """How many cases of the small matrix have MORE than 1 % of the reference's own pixels hanging
+    on the last ulps of NumPy's libm (helpers.stable_pixel_mask; e.g. an un-rotated map onto an
+    equirect source puts pixel centres exactly on row boundaries, a 360-degree stereographic lens
+    has an infinite image radius).  Counted with the oracle alone; tests/test_gpu_parity.py may
+    treat at most this many cases as "degenerate" (stable pixels only), so the constants there
+    are pinned here."""
+    import helpers
+    import test_gpu_parity as gpu_tests
+    from oracle import numpy_port
+
+    by_id = {c[0]: c for c in case_matrix.all_cases()}
+
+    def degenerate(cid, channels=3):
+        _, og, rots, sg, seed = by_id[cid]
+        image = case_matrix.case_image(sg, seed, channels)
+        try:
+            cmap = numpy_port.coordinate_map(og, rots)
+        except ValueError:
+            return False
+        return bool((~helpers.stable_pixel_mask(sg, image, cmap)).mean() > 0.01)
+
+    assert sum(degenerate(cid) for cid in by_id) == gpu_tests.MAX_DEGENERATE_MATRIX
+    with open(os.path.join(GOLDEN, "small_cases.json")) as fh:
+        meta = json.load(fh)
+    outputs = np.load(os.path.join(GOLDEN, "small_outputs.npz"))
+    n = sum(degenerate("__".join(key.split("__")[:3]), meta[key].get("channels", 3)) for key in outputs.files)
+    assert n == gpu_tests.MAX_DEGENERATE_GOLDEN
+
+
+def test_c_port_config5_frames_at_full_size():
+    """oracle/pb_oracle.c on frames of BASELINE config 5 (seeds 1234 + k, 3840x7680 double fisheye
+    -> 3840x7680 equirect): sha256-identical to the live reference's outputs
+    (tests/golden/cfg5_frames.json) -- the checker bench.py's ``parity`` block uses."""
+    from photonbend_b200 import workloads
+
+    wl = workloads.WORKLOADS["cfg5"]
+    with open(os.path.join(GOLDEN, "cfg5_frames.json")) as fh:
+        golden = json.load(fh)["frames"]
+    assert len(golden) >= 8
+    for k in (0, 3, 7):
+        image = workloads.source_image(wl, frame=k)
+        assert _sha(image) == golden[k]["src_sha256"]
+        assert _sha(c_port.remap(wl["out"], wl["rotations"], wl["src"], image)) == golden[k]["out_sha256"], k
