@@ -15,7 +15,7 @@
  *
  * Conventions as in pb_remap.h: device pointers on the CURRENT device, caller owns every buffer,
  * work is enqueued on `stream`, int return codes (PB_IO_OK = 0) + pb_io_last_error(), nothing
- * throws across the ABI.  The library keeps one nvJPEG handle per process (created on first use).
+ * throws across the ABI.  The library keeps one nvJPEG handle per device (created on first use with that device current).
  */
 #ifndef PB_IO_H
 #define PB_IO_H

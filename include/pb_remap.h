@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define PB_ABI_VERSION 1
+#define PB_ABI_VERSION 2
 
 /* image formats: projection.py CameraImage :69, DoubleCameraImage :277, PanoramaImage :465 */
 enum { PB_KIND_CAMERA = 0, PB_KIND_DOUBLE = 1, PB_KIND_EQUIRECT = 2 };
@@ -52,7 +52,10 @@ enum {
     PB_LENS_ORTHOGRAPHIC = 2,
     PB_LENS_STEREOGRAPHIC = 3,
     PB_LENS_RECTILINEAR = 4,
-    PB_LENS_THOBY = 5
+    PB_LENS_THOBY = 5,
+    /* a user-defined lens (lens.py:48-64 lets Lens wrap any pair of callables): the function the
+     * kernel needs is handed over as a table of samples, see pb_image_desc.lens_table */
+    PB_LENS_TABLE = 6
 };
 
 enum {
@@ -73,6 +76,17 @@ typedef struct pb_image_desc {
     int32_t width;     /* pixels (a double image holds two width/2 halves side by side) */
     double fov;        /* radians: full field of view (camera) or per-sensor fov (double) */
     double f_distance; /* pixels per focal unit = magnitude / lens_forward(fov / 2) */
+    /* PB_LENS_TABLE only (otherwise NULL / 0): lens_table_n >= 2 float64 samples in HOST memory of
+     * the one lens function this side of the remap evaluates, at x_k = k * lens_table_max /
+     * (lens_table_n - 1): as `out`, the lens's reverse function (radius in focal units ->
+     * latitude); as `src`, its forward function (latitude -> radius in focal units).  The kernel
+     * interpolates linearly and clamps x to [0, lens_table_max].  Copied during the call (plans
+     * keep a device copy): the caller may free it afterwards.  Results follow the user's callables
+     * to the interpolation error, not bit for bit -- the only lens kind for which that holds. */
+    const double *lens_table;
+    int32_t lens_table_n;
+    int32_t reserved_;
+    double lens_table_max;
 } pb_image_desc;
 
 /* A whole remap: output geometry, rotations applied in order, source geometry. */
@@ -154,6 +168,27 @@ int pb_rotate_map_f64(const double matrix[9], double *map_in, double *map_out, i
 int pb_gather_from_map_u8(const pb_image_desc *src_desc, int32_t channels, double *map,
                           int32_t map_height, int32_t map_width, const uint8_t *src, uint8_t *dst,
                           void *stream);
+
+/*
+ * map_projection (projection.py:550-599) on an explicit map (device, float64 map_height x
+ * map_width x 3): dst (device, map_height x map_width x 3 uint8) = (latitude stretched over the
+ * range it takes on the valid pixels, longitude * 255 / 2 pi, 255 where invalid), each rounded half
+ * to even and cast like numpy's astype(uint8).  Like the reference it zeroes (lat, lon) of the
+ * invalid entries of map in place.  A map without a valid pixel makes the reference raise
+ * (numpy.min of an empty array); callers check that themselves -- here the red channel is then 0.
+ */
+int pb_map_projection_u8(double *map, int32_t map_height, int32_t map_width, uint8_t *dst, void *stream);
+
+/*
+ * Diagnostics of the FP32-first tier of the per-pixel chain (csrc/pb_fast32.cuh), over every output
+ * pixel of a geometry, synchronous: stats[0..1] = largest |float - double| / (2^-24 * error shape)
+ * of a source coordinate along x / y (the calibration of the tier's error bound K), stats[2] =
+ * pixels, stats[3] = pixels the tier left undecided (they take the float64 tiers), stats[4] = pixels
+ * it decided DIFFERENTLY from the float64 tiers (must be 0), stats[5] = pixels whose fov / no-pixel
+ * status float and double evaluations disagree on (must be 0).  No reference counterpart: the
+ * reference computes in float64 throughout (projection.py:37,46,57).
+ */
+int pb_debug_fast32_stats(const pb_remap_desc *desc, double stats[6], void *stream);
 
 #ifdef __cplusplus
 }

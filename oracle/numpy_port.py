@@ -383,3 +383,24 @@ def remap(out_geom: dict, rotations, src_geom: dict, image, rows=None):
         for pyr in rotations:
             cmap = rotate_map(cmap, rotation_matrix(*pyr))
         return sample(src_geom, image, cmap)
+
+
+def map_projection(cmap):
+    """projection.py:550-599: coordinate map -> RGB visualisation (zeroes the invalid (lat, lon) of
+    ``cmap`` in place through the view, :563-566)."""
+    rgb_range = 255.0
+    invalid = cmap[:, :, 2] != 0.0
+    valid = np.logical_not(invalid)
+    polar = cmap[:, :, :2]
+    polar[invalid] = 0
+    distance = polar[:, :, 0]
+    lo = np.min(distance[valid])
+    hi = np.max(distance[valid])
+    factor = rgb_range / (hi - lo)
+    red = distance.copy()
+    red[valid] -= lo
+    red[valid] *= factor
+    red8 = np.round(red).astype(np.uint8)
+    green8 = np.round(rgb_range / (np.pi * 2) * polar[:, :, 1]).astype(np.uint8)
+    blue8 = (invalid.astype(np.uint8) * 255).astype(np.uint8)
+    return np.concatenate([red8[:, :, None], green8[:, :, None], blue8[:, :, None]], axis=2)

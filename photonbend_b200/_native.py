@@ -16,7 +16,8 @@ PB_MAX_ROTATIONS = 16
 
 KIND_CAMERA, KIND_DOUBLE, KIND_EQUIRECT = 0, 1, 2
 (LENS_EQUIDISTANT, LENS_EQUISOLID, LENS_ORTHOGRAPHIC, LENS_STEREOGRAPHIC, LENS_RECTILINEAR,
- LENS_THOBY) = range(6)
+ LENS_THOBY, LENS_TABLE) = range(7)
+PB_ABI_VERSION = 2
 
 PB_OK = 0
 PB_ERR_INVALID_ARGUMENT = 1
@@ -38,6 +39,8 @@ EXPORTS = (
     "pb_materialize_map_f64",
     "pb_rotate_map_f64",
     "pb_gather_from_map_u8",
+    "pb_map_projection_u8",
+    "pb_debug_fast32_stats",
 )
 
 
@@ -49,6 +52,10 @@ class ImageDesc(ctypes.Structure):
         ("width", ctypes.c_int32),
         ("fov", ctypes.c_double),
         ("f_distance", ctypes.c_double),
+        ("lens_table", ctypes.POINTER(ctypes.c_double)),  # LENS_TABLE: host samples of the lens function
+        ("lens_table_n", ctypes.c_int32),
+        ("reserved_", ctypes.c_int32),
+        ("lens_table_max", ctypes.c_double),
     ]
 
 
@@ -109,6 +116,10 @@ def load():
     lib.pb_rotate_map_f64.argtypes = [ctypes.POINTER(ctypes.c_double), vp, vp, i64, vp]
     lib.pb_gather_from_map_u8.restype = ctypes.c_int
     lib.pb_gather_from_map_u8.argtypes = [ctypes.POINTER(ImageDesc), i32, vp, i32, i32, vp, vp, vp]
+    lib.pb_map_projection_u8.restype = ctypes.c_int
+    lib.pb_map_projection_u8.argtypes = [vp, i32, i32, vp, vp]
+    lib.pb_debug_fast32_stats.restype = ctypes.c_int
+    lib.pb_debug_fast32_stats.argtypes = [ctypes.POINTER(RemapDesc), ctypes.POINTER(ctypes.c_double), vp]
     _lib = lib
     return lib
 

@@ -4,9 +4,11 @@ reference's photonbend/core/lens.py (Lens :48-64, factories :341-401).
 The host callables below serve two purposes only: deriving the focal distance of an image
 (``f = magnitude / forward(fov / 2)``, a scalar) and being handed to users who call them.  The
 per-pixel evaluation happens in the CUDA kernel, which recognises the six built-in models by
-the identity of these function objects (``lens_id``).  A user-supplied callable cannot be fused
-into the kernel and is rejected with NotImplementedError at projection time -- there is no CPU
-fallback.
+the identity of these function objects (``lens_id``).  A user-supplied callable (the reference's
+Lens wraps any pair of callables, lens.py:48-64) cannot be compiled into the kernel; it is sampled
+on the host once per image (``lens_table``) and the kernel interpolates the table (PB_LENS_TABLE) --
+the one case whose pixels follow the reference to the interpolation error (~1e-7 px for smooth
+functions) instead of bit for bit.
 """
 
 from __future__ import annotations
@@ -135,15 +137,30 @@ _BUILTIN = {
 
 
 def lens_id(forward_function, reverse_function) -> int:
-    """The kernel's id of a built-in lens pair; NotImplementedError for anything else."""
+    """The kernel's id of a lens pair: one of the six built-in models, or LENS_TABLE for
+    user-defined callables (sampled with ``lens_table``)."""
     for ident, (fwd, inv) in _BUILTIN.items():
         if forward_function is fwd and reverse_function is inv:
             return ident
-    raise NotImplementedError(
-        "only the built-in lens models (equidistant, equisolid, orthographic, stereographic, "
-        "rectilinear, thoby) run on the B200 path; a custom Lens callable cannot be fused into "
-        "the kernel and there is no CPU fallback"
-    )
+    return _native.LENS_TABLE
+
+
+LENS_TABLE_SAMPLES = 65537
+
+
+def lens_table(function, x_max: float, samples: int = LENS_TABLE_SAMPLES) -> np.ndarray:
+    """float64 samples of a user-defined lens function on [0, x_max] (it is called with an array,
+    as the reference calls it: lens.py docstrings, projection.py:189, 251).  With 65537 samples
+    the kernel's linear interpolation is within x_max^2 / 2^35 * max|f''| of the function."""
+    if not (np.isfinite(x_max) and x_max > 0):
+        raise ValueError("lens_table needs a positive, finite range")
+    xs = np.linspace(0.0, float(x_max), int(samples))
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ys = np.asarray(function(xs), dtype=np.float64)
+    if ys.shape != xs.shape:
+        raise ValueError("a lens function must map an array of angles / radii to an array of the same shape")
+    return np.ascontiguousarray(ys)
 
 
 def rectilinear() -> Lens:

@@ -21,7 +21,7 @@ import numpy as np
 
 from photonbend_b200 import _native, engine
 from photonbend_b200.core.coordinate_map import CoordinateMap
-from photonbend_b200.core.lens import Lens, lens_id
+from photonbend_b200.core.lens import Lens, lens_id, lens_table
 
 
 class ProjectionImage(Protocol):
@@ -46,6 +46,26 @@ def _frame_shape(image):
     if len(shape) == 4:
         return shape[1], shape[2]
     return shape[0], shape[1]
+
+
+def _custom_lens_table(image, lens: int, role: str, height: int, width: int):
+    """(samples, range) of the lens function a user-defined Lens needs on this side of a remap --
+    as a source the forward function on [0, pi] (latitudes), as an output the reverse function on
+    [0, largest pixel radius in focal units] -- cached on the image object; (None, 0) for the
+    built-in models."""
+    if lens != _native.LENS_TABLE:
+        return None, 0.0
+    cache = image.__dict__.setdefault("_lens_tables", {})
+    key = (role, height, width, float(image.f_distance))
+    if key not in cache:
+        if role == "source":
+            x_max = float(np.pi)
+            fn = image.forward_lens
+        else:
+            x_max = float(np.hypot((width - 1) / 2.0, (height - 1) / 2.0) / image.f_distance) * (1.0 + 1e-9) + 1e-12
+            fn = image.reverse_lens
+        cache[key] = (lens_table(fn, x_max), x_max)
+    return cache[key]
 
 
 class _DeviceSampler:
@@ -141,15 +161,19 @@ class CameraImage(_DeviceSampler):
         forward function raises ValueError here for fov / 2 > 89 degrees.)"""
         return self.magnitude / self.forward_lens(self.fov / 2)
 
-    def _geometry(self) -> engine.ImageGeometry:
+    def _geometry(self, role: str) -> engine.ImageGeometry:
         height, width = _frame_shape(self.image)
+        lens = lens_id(self.forward_lens, self.reverse_lens)
+        table, table_max = _custom_lens_table(self, lens, role, height, width)
         return engine.ImageGeometry(
-            kind=_native.KIND_CAMERA, height=height, width=width,
-            lens=lens_id(self.forward_lens, self.reverse_lens),
-            fov=float(self.fov), f_distance=float(self.f_distance))
+            kind=_native.KIND_CAMERA, height=height, width=width, lens=lens,
+            fov=float(self.fov), f_distance=float(self.f_distance), table=table, table_max=table_max)
 
-    _source_geometry = _geometry
-    _output_geometry = _geometry
+    def _source_geometry(self):
+        return self._geometry("source")
+
+    def _output_geometry(self):
+        return self._geometry("output")
 
 
 class DoubleCameraImage(_DeviceSampler):
@@ -175,15 +199,19 @@ class DoubleCameraImage(_DeviceSampler):
     def _compute_f_distance(self) -> float:
         return self.magnitude / self.forward_lens(self.sensor_fov / 2)
 
-    def _geometry(self) -> engine.ImageGeometry:
+    def _geometry(self, role: str) -> engine.ImageGeometry:
         height, width = _frame_shape(self.image)
+        lens = lens_id(self.forward_lens, self.reverse_lens)
+        table, table_max = _custom_lens_table(self, lens, role, height, width // 2)
         return engine.ImageGeometry(
-            kind=_native.KIND_DOUBLE, height=height, width=width,
-            lens=lens_id(self.forward_lens, self.reverse_lens),
-            fov=float(self.sensor_fov), f_distance=float(self.f_distance))
+            kind=_native.KIND_DOUBLE, height=height, width=width, lens=lens,
+            fov=float(self.sensor_fov), f_distance=float(self.f_distance), table=table, table_max=table_max)
 
-    _source_geometry = _geometry
-    _output_geometry = _geometry
+    def _source_geometry(self):
+        return self._geometry("source")
+
+    def _output_geometry(self):
+        return self._geometry("output")
 
 
 class PanoramaImage(_DeviceSampler):
@@ -205,20 +233,24 @@ class PanoramaImage(_DeviceSampler):
 
 
 def map_projection(coordinate_map) -> np.ndarray:
-    """Visualise a coordinate map as an RGB image: latitude -> red, longitude -> green,
-    invalid -> blue (debug helper of the reference, projection.py:550-599; host-side, not part
-    of the remap path)."""
-    cmap = np.array(coordinate_map, dtype=np.float64)
-    invalid = cmap[:, :, 2] != 0.0
-    valid = ~invalid
-    cmap[invalid, :2] = 0
-    lat = cmap[:, :, 0]
-    lo, hi = np.min(lat[valid]), np.max(lat[valid])
-    red = lat.copy()
-    red[valid] = (red[valid] - lo) * (255.0 / (hi - lo))
-    green = cmap[:, :, 1] * (255.0 / (np.pi * 2))
-    out = np.empty(cmap.shape[:2] + (3,), dtype=np.uint8)
-    out[:, :, 0] = np.round(red).astype(np.uint8)
-    out[:, :, 1] = np.round(green).astype(np.uint8)
-    out[:, :, 2] = invalid.astype(np.uint8) * 255
-    return out
+    """Visualise a coordinate map as an RGB image: latitude -> red (stretched over the range it
+    takes on the valid pixels), longitude -> green, invalid -> blue (the reference's debug helper,
+    projection.py:550-599).  Runs on the GPU (pb_map_projection_u8): a lazy CoordinateMap is
+    materialised on the device and never visits the host; an ndarray is uploaded.  Like the
+    reference, (lat, lon) of the invalid entries of an ndarray argument are zeroed in place."""
+    torch = engine._torch()
+    if isinstance(coordinate_map, CoordinateMap) and coordinate_map.is_lazy:
+        dev = engine.materialize_map_device(coordinate_map.rays)
+        coordinate_map._mark_invalid_zeroed()
+    elif engine.is_torch_tensor(coordinate_map) and coordinate_map.is_cuda:
+        dev = coordinate_map  # zeroed in place by the kernel
+    else:
+        arr = coordinate_map.materialize() if isinstance(coordinate_map, CoordinateMap) else coordinate_map
+        if not (isinstance(arr, np.ndarray) and arr.dtype == np.float64 and arr.ndim == 3 and arr.shape[2] == 3):
+            raise ValueError("coordinate map must be float64 of shape (H, W, 3)")
+        dev = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+        arr[arr[:, :, 2] != 0.0, :2] = 0  # projection.py:566 writes through a view of the caller's map
+    if not bool((dev[:, :, 2] == 0).any()):
+        # numpy.min of an empty selection (projection.py:570)
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    return engine.map_projection_device(dev).cpu().numpy()

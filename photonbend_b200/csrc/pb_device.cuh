@@ -31,6 +31,9 @@ struct OutGeom {
     double x_start, x_stop, x_step;  // camera/double: x of a column        projection.py:177, 390-392
     double y_start, y_stop, y_step;  // camera/double: y of a row           projection.py:178-180, 399-401
                                      // equirect: x = longitude, y = latitude projection.py:502-505
+    const double* lut;               // PB_LENS_TABLE: device samples of the reverse lens function
+    double lut_scale;                // (n - 1) / x_max
+    int lut_n;
 };
 
 struct SrcGeom {
@@ -43,6 +46,9 @@ struct SrcGeom {
     double rect_limit;    // to_radians(89), rectilinear forward domain      lens.py:97-98
     double seg_h, seg_w, half_w;  // equirect: pi/H, pi/(W/2), W/2           projection.py:538-543
     double mrg_lo, mrg_hi, mrg_hi_safe, mrg_span;  // double blend band      projection.py:414-418
+    const double* lut;    // PB_LENS_TABLE: device samples of the forward lens function
+    double lut_scale;     // (n - 1) / x_max
+    int lut_n;
 };
 
 struct Rotations {
@@ -81,8 +87,23 @@ __device__ __forceinline__ long long floor_mod(long long a, long long m) {
 
 // ---------------------------------------------------------------------------------- lenses
 
+// A user-defined lens function from its table of samples (PB_LENS_TABLE): linear interpolation,
+// x clamped to the table's range; NaN stays NaN.
+__device__ __forceinline__ double lens_table_at(const double* __restrict__ lut, double scale, int n, double x) {
+    if (x != x) return x;
+    double t = x * scale;
+    t = t < 0.0 ? 0.0 : t;
+    int i = t >= (double)(n - 1) ? n - 2 : (int)t;
+    const double a = __ldg(lut + i), b = __ldg(lut + i + 1);
+    const double fr = fmin(t - (double)i, 1.0);
+    return a + (b - a) * fr;
+}
+
 // lens.py:75-103, 126-144, 168-187, 224-243, 266-286, 313-335 (array branch)
-__device__ __forceinline__ double lens_forward(int lens, double theta, double rect_limit) {
+__device__ __forceinline__ double lens_forward(const SrcGeom& s, double theta) {
+    const int lens = s.lens;
+    const double rect_limit = s.rect_limit;
+    if (lens == PB_LENS_TABLE) return lens_table_at(s.lut, s.lut_scale, s.lut_n, theta);
     switch (lens) {
         case PB_LENS_EQUIDISTANT: return theta;
         case PB_LENS_EQUISOLID: return 2.0 * sin(theta / 2.0);
@@ -96,7 +117,9 @@ __device__ __forceinline__ double lens_forward(int lens, double theta, double re
 }
 
 // lens.py:68-72, 106-124, 147-165, 190-220, 246-262, 289-309
-__device__ __forceinline__ double lens_inverse(int lens, double d) {
+__device__ __forceinline__ double lens_inverse(const OutGeom& g, double d) {
+    const int lens = g.lens;
+    if (lens == PB_LENS_TABLE) return lens_table_at(g.lut, g.lut_scale, g.lut_n, d);
     switch (lens) {
         case PB_LENS_EQUIDISTANT: return d;
         case PB_LENS_EQUISOLID: {
@@ -132,7 +155,7 @@ __device__ __forceinline__ Ray output_ray(const OutGeom& g, int i, int j) {
         if (right) x = __dmul_rn(x, -1.0);
         const double y = linspace_at(g.y_start, g.y_stop, g.y_step, g.H, i);
         const double d = __ddiv_rn(sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y))), g.f);
-        double lat = lens_inverse(g.lens, d);
+        double lat = lens_inverse(g, d);
         if (right) {
             lat = __dadd_rn(__dmul_rn(lat, -1.0), kPi);
             r.invalid = lat < g.right_lat_min;
@@ -208,9 +231,9 @@ __device__ __forceinline__ int camera_xy_from(double c, double s, double dist, i
     return pack_xy(trunc_index(fx, w), trunc_index(fy, h), col0, w, flip);
 }
 
-__device__ __forceinline__ int camera_xy(int lens, double f, double rect_limit, int h, int w, double cy,
+__device__ __forceinline__ int camera_xy(const SrcGeom& g, int h, int w, double cy,
                                          double cx, double lat, double lon, int col0, bool flip) {
-    const double dist = __dmul_rn(lens_forward(lens, lat, rect_limit), f);
+    const double dist = __dmul_rn(lens_forward(g, lat), g.f);
     double s, c;
     sincos(lon, &s, &c);
     return camera_xy_from(c, s, dist, h, w, cy, cx, col0, flip);
@@ -239,7 +262,7 @@ __device__ __forceinline__ Lookup source_lookup(const SrcGeom& s, Ray r) {
     L.w0 = L.w1 = 1.0;
     if (r.invalid) return L;
     if (SRC_KIND == PB_KIND_CAMERA) {
-        L.xy0 = camera_xy(s.lens, s.f, s.rect_limit, s.H, s.W, s.cy, s.cx, r.lat, r.lon, 0, false);
+        L.xy0 = camera_xy(s, s.H, s.W, s.cy, s.cx, r.lat, r.lon, 0, false);
     } else if (SRC_KIND == PB_KIND_EQUIRECT) {
         // a11 projection.py:515-547: true division, truncation, Python-sign modulo
         const int row = wrap_index(__ddiv_rn(r.lat, s.seg_h), s.H);
@@ -251,8 +274,8 @@ __device__ __forceinline__ Lookup source_lookup(const SrcGeom& s, Ray r) {
         const double lat_r = __dadd_rn(__dmul_rn(r.lat, -1.0), kPi);
         double sn, cs;
         sincos(r.lon, &sn, &cs);
-        const double dist_l = __dmul_rn(lens_forward(s.lens, lat_l, s.rect_limit), s.f);
-        const double dist_r = __dmul_rn(lens_forward(s.lens, lat_r, s.rect_limit), s.f);
+        const double dist_l = __dmul_rn(lens_forward(s, lat_l), s.f);
+        const double dist_r = __dmul_rn(lens_forward(s, lat_r), s.f);
         L.xy0 = camera_xy_from(cs, sn, dist_l, s.H, s.wl, s.cy, s.cxl, 0, false);
         L.xy1 = camera_xy_from(cs, sn, dist_r, s.H, s.wr, s.cy, s.cxr, s.wl, true);
         L.w0 = merge_weight(s, lat_l);

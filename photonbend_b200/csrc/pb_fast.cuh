@@ -34,6 +34,54 @@
 
 namespace pb {
 
+// T = float: what the kernels use; T = double: the same constants unrounded, for the calibration
+// reference (so that the rounding of the constants themselves is part of the measured error)
+template <typename T>
+struct Fast32GeomT {
+    int enabled;
+    int has_rot;
+    T rot[9];
+    // output side, camera / double: x = col + x0 (col counted within the half), y = y0 - row
+    T x0, y0;
+    T inv_f, quarter_inv_f2;  // 1 / f, 0.25 / f^2
+    T r2_valid, r2_invalid, r2_domain;
+    // output side, equirect: lon = col * lon_step + lon0, lat = row * lat_step
+    T lon0, lon_step, lat_step;
+    // source side
+    T src_f;
+    T inv_seg_h, inv_seg_w;    // equirect source: rows / columns per radian
+    T ny_rect_in, ny_rect_out;
+    T ny_band_lo, ny_band_hi;
+    T k_eps;                   // K * 2^-24
+};
+using Fast32Geom = Fast32GeomT<float>;
+
+inline Fast32Geom fast32_to_float(const Fast32GeomT<double>& d) {
+    Fast32Geom f;
+    f.enabled = d.enabled;
+    f.has_rot = d.has_rot;
+    for (int e = 0; e < 9; ++e) f.rot[e] = (float)d.rot[e];
+    f.x0 = (float)d.x0;
+    f.y0 = (float)d.y0;
+    f.inv_f = (float)d.inv_f;
+    f.quarter_inv_f2 = (float)d.quarter_inv_f2;
+    f.r2_valid = (float)d.r2_valid;
+    f.r2_invalid = (float)d.r2_invalid;
+    f.r2_domain = (float)d.r2_domain;
+    f.lon0 = (float)d.lon0;
+    f.lon_step = (float)d.lon_step;
+    f.lat_step = (float)d.lat_step;
+    f.src_f = (float)d.src_f;
+    f.inv_seg_h = (float)d.inv_seg_h;
+    f.inv_seg_w = (float)d.inv_seg_w;
+    f.ny_rect_in = (float)d.ny_rect_in;
+    f.ny_rect_out = (float)d.ny_rect_out;
+    f.ny_band_lo = (float)d.ny_band_lo;
+    f.ny_band_hi = (float)d.ny_band_hi;
+    f.k_eps = (float)d.k_eps;
+    return f;
+}
+
 struct FastGeom {
     int enabled;
     int n_rot;
@@ -48,6 +96,7 @@ struct FastGeom {
     double inv_seg_h, inv_seg_w;   // equirect source: rows / columns per radian
     double ny_rect_in, ny_rect_out;  // rectilinear source lens: cos(lat) > in: tan defined; < out: NaN (no pixel)
     double ny_band_lo, ny_band_hi;   // double source: cos(lat) in [lo, hi] may be blended -> undecided
+    Fast32Geom f32;                  // the FP32-first tier in front of this one (pb_fast32.cuh)
 };
 
 constexpr double kTwo52 = 4503599627370496.0;
@@ -311,14 +360,6 @@ __device__ __noinline__ Lookup exact_lookup(const OutGeom& out, const Rotations&
     Ray r = output_ray<OUT_KIND>(out, i, j);
     for (int n = 0; n < rot.n; ++n) r = rotate_ray(r, rot.m[n]);
     return source_lookup<SRC_KIND>(src, r);
-}
-
-template <int OUT_KIND, int SRC_KIND>
-__device__ __forceinline__ Lookup resolve_lookup(const OutGeom& out, const FastGeom& fg, const Rotations& rot,
-                                                 const SrcGeom& src, int i, int j) {
-    Lookup L;
-    if (fg.enabled && fast_lookup<OUT_KIND, SRC_KIND>(out, fg, rot, src, i, j, L)) return L;
-    return exact_lookup<OUT_KIND, SRC_KIND>(out, rot, src, i, j);
 }
 
 }  // namespace pb

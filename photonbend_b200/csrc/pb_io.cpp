@@ -42,8 +42,9 @@ int codec_fail(nvjpegStatus_t s, const char* what) {
                 std::string(what) + ": nvjpeg " + status_name(s));
 }
 
-// one handle, one decoder state and one encoder state per process, serialised by a mutex: the
-// callers (CLI commands, a frame loop) decode / encode one image at a time
+// one handle, one decoder state and one encoder state per DEVICE (created on first use with that
+// device current), each serialised by its own mutex: a caller decodes / encodes one image at a
+// time per GPU; the host threads that drive different GPUs do not wait for each other
 struct Codec {
     std::mutex lock;
     nvjpegHandle_t handle = nullptr;
@@ -68,9 +69,13 @@ struct Codec {
     }
 };
 
+constexpr int kMaxDevices = 64;
+
 Codec& codec() {
-    static Codec c;  // never destroyed: the CUDA context may already be gone at exit
-    return c;
+    static Codec* c = new Codec[kMaxDevices];  // never destroyed: the CUDA context may already be gone at exit
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return c[dev];
 }
 
 }  // namespace

@@ -101,6 +101,16 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
     return p;
 }
 
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// 0 = evict_last, 1 = evict_normal, 2 = evict_first
+__device__ __forceinline__ uint64_t policy_of(int k) {
+    return k == 0 ? policy_evict_last() : k == 1 ? policy_evict_normal() : policy_evict_first();
+}
+
 __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar,
                                                  uint64_t policy) {
     asm volatile(

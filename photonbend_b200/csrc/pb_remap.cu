@@ -17,6 +17,7 @@
 #include "pb_device.cuh"
 #include "pb_tiled.cuh"
 #include "pb_sep1.cuh"
+#include "pb_chunk.cuh"
 
 namespace pb {
 
@@ -53,8 +54,12 @@ static int check_image(const pb_image_desc& d, const char* which) {
         return fail(PB_ERR_INVALID_ARGUMENT, std::string(which) + ": height and width must be positive");
     if ((long long)d.height * (long long)d.width >= (1LL << 31))
         return fail(PB_ERR_UNSUPPORTED, std::string(which) + ": more than 2^31 pixels");
-    if (d.kind != PB_KIND_EQUIRECT && (d.lens < PB_LENS_EQUIDISTANT || d.lens > PB_LENS_THOBY))
+    if (d.kind != PB_KIND_EQUIRECT && (d.lens < PB_LENS_EQUIDISTANT || d.lens > PB_LENS_TABLE))
         return fail(PB_ERR_INVALID_ARGUMENT, std::string(which) + ": unknown lens");
+    if (d.kind != PB_KIND_EQUIRECT && d.lens == PB_LENS_TABLE &&
+        (!d.lens_table || d.lens_table_n < 2 || d.lens_table_n > (1 << 24) || !(d.lens_table_max > 0.0) ||
+         !std::isfinite(d.lens_table_max)))
+        return fail(PB_ERR_INVALID_ARGUMENT, std::string(which) + ": PB_LENS_TABLE needs lens_table (>= 2 samples) and lens_table_max > 0");
     if (d.kind == PB_KIND_DOUBLE && d.width < 2)
         return fail(PB_ERR_INVALID_ARGUMENT, std::string(which) + ": a double image needs width >= 2");
     return PB_OK;
@@ -131,6 +136,40 @@ static SrcGeom derive_src(const pb_image_desc& d, int channels) {
     return s;
 }
 
+static bool has_table(const pb_image_desc& d) { return d.kind != PB_KIND_EQUIRECT && d.lens == PB_LENS_TABLE; }
+
+// Device copies of the lens tables of a remap (PB_LENS_TABLE), one allocation: *dev owns them.
+// The host tables are pageable memory: the copies are staged before the call returns, so the caller
+// may free its tables afterwards.
+static cudaError_t upload_lens_tables(const pb_image_desc* od, OutGeom* og, const pb_image_desc* sd, SrcGeom* sg,
+                                      double** dev, cudaStream_t st, bool stream_ordered) {
+    *dev = nullptr;
+    const size_t n_out = (od && og && has_table(*od)) ? (size_t)od->lens_table_n : 0;
+    const size_t n_src = (sd && sg && has_table(*sd)) ? (size_t)sd->lens_table_n : 0;
+    if (n_out + n_src == 0) return cudaSuccess;
+    cudaError_t e = stream_ordered ? cudaMallocAsync((void**)dev, (n_out + n_src) * sizeof(double), st)
+                                   : cudaMalloc((void**)dev, (n_out + n_src) * sizeof(double));
+    if (e != cudaSuccess) return e;
+    if (n_out) {
+        e = cudaMemcpyAsync(*dev, od->lens_table, n_out * sizeof(double), cudaMemcpyHostToDevice, st);
+        og->lut = *dev;
+        og->lut_n = (int)n_out;
+        og->lut_scale = (double)(n_out - 1) / od->lens_table_max;
+    }
+    if (n_src && e == cudaSuccess) {
+        e = cudaMemcpyAsync(*dev + n_out, sd->lens_table, n_src * sizeof(double), cudaMemcpyHostToDevice, st);
+        sg->lut = *dev + n_out;
+        sg->lut_n = (int)n_src;
+        sg->lut_scale = (double)(n_src - 1) / sd->lens_table_max;
+    }
+    if (e != cudaSuccess) {
+        if (stream_ordered) cudaFreeAsync(*dev, st);
+        else cudaFree(*dev);
+        *dev = nullptr;
+    }
+    return e;
+}
+
 // Constants of the guarded short cut (pb_fast.cuh).  Nothing here has to be bit-identical to
 // the reference: these are decision thresholds with a guard band, not values that reach a pixel.
 static FastGeom derive_fast(const pb_image_desc& od, const OutGeom& o, const pb_image_desc& sd, const SrcGeom& s,
@@ -141,6 +180,7 @@ static FastGeom derive_fast(const pb_image_desc& od, const OutGeom& o, const pb_
     const double rel = 1e-9;  // relative guard on angles and radii
     g.n_rot = n_rot;
     g.enabled = 1;
+    if (has_table(od) || has_table(sd)) g.enabled = 0;  // a user-defined lens has no algebraic form: exact chain
     // R_total = R_n ... R_1: the short cut applies all rotations as one matrix
     double acc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     for (int k = 0; k < n_rot; ++k) {
@@ -229,9 +269,87 @@ static FastGeom derive_fast(const pb_image_desc& od, const OutGeom& o, const pb_
             }
         }
     }
-    (void)od;
-    (void)sd;
     return g;
+}
+
+// Constants of the FP32-first tier (pb_fast32.cuh): decision thresholds with guards sized for float
+// arithmetic.  d: the unrounded constants (calibration reference); the kernels get the float copy.
+// K (error bound = K * 2^-24 * shape) was calibrated with pb_debug_fast32_stats: see
+// tests/test_gpu_parity.py::test_fp32_tier_error_bound for the ratios measured.
+constexpr double kFast32K = 16.0;
+
+static Fast32GeomT<double> derive_fast32(const OutGeom& o, const SrcGeom& s, const FastGeom& g) {
+    Fast32GeomT<double> d;
+    std::memset(&d, 0, sizeof(d));
+    const double inf = INFINITY;
+    d.enabled = g.enabled;
+    if (const char* e = std::getenv("PB_FP32")) {
+        if (std::atoi(e) == 0) d.enabled = 0;
+    }
+    // index32 keeps coordinates below 2^21; float pixel-centre coordinates must be exact
+    if (o.H > (1 << 20) || o.W > (1 << 20) || s.H > (1 << 20) || s.W > (1 << 20)) d.enabled = 0;
+    d.has_rot = g.has_rot;
+    std::memcpy(d.rot, g.rot, sizeof(d.rot));
+    d.r2_valid = d.r2_invalid = d.r2_domain = inf;
+    if (o.kind == PB_KIND_EQUIRECT) {
+        d.lon0 = o.x_start;
+        d.lon_step = o.x_step;
+        d.lat_step = o.y_step;
+    } else {
+        const double f = o.f, hf = o.half_fov, rel = 2e-5;
+        d.x0 = o.x_start;
+        d.y0 = o.y_start;
+        d.inv_f = 1.0 / f;
+        d.quarter_inv_f2 = 0.25 / (f * f);
+        double d_star = inf;
+        switch (o.lens) {
+            case PB_LENS_EQUIDISTANT: d_star = hf; break;
+            case PB_LENS_EQUISOLID: d_star = hf < kPi ? 2.0 * std::sin(hf / 2.0) : inf; break;
+            case PB_LENS_ORTHOGRAPHIC: d_star = hf < kPi / 2 ? std::sin(hf) : inf; break;
+            case PB_LENS_STEREOGRAPHIC: d_star = hf < kPi ? 2.0 * std::tan(hf / 2.0) : inf; break;
+            case PB_LENS_RECTILINEAR: d_star = hf < kPi / 2 ? std::tan(hf) : inf; break;
+            default: d_star = 0.713 * hf < kPi / 2 ? 1.47 * std::sin(0.713 * hf) : inf; break;
+        }
+        if (hf < 0.0) {
+            d.r2_valid = d.r2_invalid = -1.0;
+        } else if (d_star < inf) {
+            const double r_star = d_star * f;
+            d.r2_valid = (r_star * (1.0 - rel)) * (r_star * (1.0 - rel));
+            d.r2_invalid = (r_star * (1.0 + rel)) * (r_star * (1.0 + rel));
+        }
+        // Lens inverses lose accuracy towards the edge of their domain (sqrt(1 - u) has a relative
+        // error of eps / (2 (1 - u))): tier 1 stops where that amplification reaches ~4, the rest of
+        // the image circle goes to the float64 tiers.  (Measured with the edge at 1 - 1e-3: error
+        // ratios of 13 on a 360-degree equisolid output against 2-6 everywhere else.)
+        switch (o.lens) {
+            case PB_LENS_EQUISOLID: d.r2_domain = 4.0 * f * f * 0.88; break;      // lat < 139 deg
+            case PB_LENS_ORTHOGRAPHIC: d.r2_domain = f * f * 0.94; break;          // lat < 76 deg
+            case PB_LENS_THOBY: d.r2_domain = 1.47 * 1.47 * f * f * 0.94; break;
+            case PB_LENS_EQUIDISTANT: d.r2_domain = (kPi * 0.999 * f) * (kPi * 0.999 * f); break;
+            default: break;
+        }
+    }
+    d.src_f = s.f;
+    d.ny_band_lo = 2.0;
+    d.ny_band_hi = -2.0;
+    if (s.kind == PB_KIND_EQUIRECT) {
+        d.inv_seg_h = 1.0 / s.seg_h;
+        d.inv_seg_w = 1.0 / s.seg_w;
+    } else {
+        const double c = std::cos(s.rect_limit), guard = 1e-5;  // absolute guards on cos(lat)
+        d.ny_rect_in = c + guard;
+        d.ny_rect_out = c - guard;
+        if (s.kind == PB_KIND_DOUBLE && s.mrg_lo <= s.mrg_hi_safe) {
+            const double t_lo = std::fmin(s.mrg_lo, kPi - s.mrg_hi_safe);
+            const double t_hi = std::fmax(s.mrg_hi_safe, kPi - s.mrg_lo);
+            d.ny_band_hi = std::cos(std::fmax(t_lo, 0.0)) + guard;
+            d.ny_band_lo = std::cos(std::fmin(t_hi, kPi)) - guard;
+        }
+    }
+    double k = kFast32K;
+    if (const char* e = std::getenv("PB_FP32_K")) k = std::atof(e);  // calibration experiments
+    d.k_eps = k * 5.9604644775390625e-08;  // K * 2^-24
+    return d;
 }
 
 // ------------------------------------------------------------------------------------ kernels
@@ -339,6 +457,99 @@ __global__ void __launch_bounds__(256, PB_DIRECT_MIN_CTAS) remap_direct_kernel(c
     }
 }
 
+// The same for a camera / panorama source with the undecided pixels of a warp COMPACTED: every
+// thread first runs tier 1 (float, pb_fast32.cuh) on its 8 pixels and parks the results in shared
+// memory; the ~1 % of pixels tier 1 could not decide are queued per warp, and the warp then works
+// the queue off with all lanes busy -- lane t takes entry t, whoever's pixel it is -- through the
+// float64 tiers.  Run in place, a pixel in a hundred would put 1 - 0.99^32 = 27 % of the warps
+// through the float64 code with one active lane.
+template <int OUT_KIND, int SRC_KIND>
+__global__ void __launch_bounds__(256, PB_DIRECT_MIN_CTAS) remap_direct32_kernel(const __grid_constant__ RemapArgs a) {
+    static_assert(SRC_KIND != PB_KIND_DOUBLE, "single-slot sources only");
+    __shared__ unsigned char queue[8][256];  // per warp: owner lane | pixel << 5
+    __shared__ int xybuf[8][kPxPerThread][32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int row0 = a.row_begin + blockIdx.y * kTileH, col0 = blockIdx.x * kTileW;
+    const int i0 = row0 + (tid >> 3), j0 = col0 + 4 * (tid & 7);
+    int qn = 0;
+#pragma unroll 1
+    for (int p = 0; p < kPxPerThread; ++p) {
+        const int i = i0 + (p >> 2) * 32, j = j0 + (p & 3);
+        bool need = false;
+        int xy = kNoPixel;
+        if (i < a.row_end && j < a.out.W) {
+            Lookup L;
+            if (a.fast.f32.enabled && fast32_lookup<OUT_KIND, SRC_KIND>(a.out, a.fast.f32, a.src, i, j, L)) xy = L.xy0;
+            else need = true;
+        }
+        xybuf[w][p][lane] = xy;
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (need) queue[w][qn + __popc(m & ((1u << lane) - 1u))] = (unsigned char)(lane | (p << 5));
+        qn += __popc(m);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int b = 0; b < qn; b += 32) {
+        const int e = b + lane;
+        if (e < qn) {
+            const int code = queue[w][e];
+            const int ot = w * 32 + (code & 31), p = code >> 5;
+            const int i = row0 + (ot >> 3) + (p >> 2) * 32, j = col0 + 4 * (ot & 7) + (p & 3);
+            xybuf[w][p][code & 31] = resolve_lookup64<OUT_KIND, SRC_KIND>(a.out, a.fast, a.rot, a.src, i, j).xy0;
+        }
+    }
+    __syncwarp();
+    if (j0 >= a.out.W) return;
+    const unsigned char* __restrict__ sp = a.src_px;
+    const int src_pitch = a.src.W * 3;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int i = i0 + q * 32;
+        if (i >= a.row_end) break;
+        unsigned px[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xy = xybuf[w][q * 4 + k][lane];
+            px[k] = xy >= 0 ? pick_px_global(sp, (xy >> 16) * src_pitch + (xy & 0xffff) * 3) : 0u;
+        }
+        store_quad(reinterpret_cast<unsigned*>(a.dst_px + ((long long)(i - a.row_begin) * a.out.W + j0) * 3), px);
+    }
+}
+
+// Calibration / self-check of tier 1 over every pixel of a geometry (pb_debug_fast32_stats):
+// stats[0..1] = largest |float - double| / (2^-24 * shape) of a coordinate (x, y) as float bits,
+// counters: [0] pixels, [1] undecided by tier 1, [2] decided by tier 1 but different from tiers 2/3,
+// [3] float and double evaluations disagree on a pixel's status (fov / no-pixel decisions)
+template <int OUT_KIND, int SRC_KIND>
+__global__ void __launch_bounds__(256) fast32_stats_kernel(const __grid_constant__ RemapArgs a,
+                                                           const __grid_constant__ Fast32GeomT<double> gd,
+                                                           unsigned* __restrict__ maxima,
+                                                           unsigned long long* __restrict__ counters) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= a.out.H || j >= a.out.W) return;
+    const Coords32<float> cf = coords32<float, OUT_KIND, SRC_KIND>(a.out, a.fast.f32, a.src, i, j);
+    const Coords32<double> cd = coords32<double, OUT_KIND, SRC_KIND>(a.out, gd, a.src, i, j);
+    const double eps = 5.9604644775390625e-08;
+    if (cf.status == 0 && cd.status == 0) {
+        atomicMax(maxima + 0, __float_as_uint((float)(fabs((double)cf.vx - cd.vx) / (eps * (double)cf.ex))));
+        atomicMax(maxima + 1, __float_as_uint((float)(fabs((double)cf.vy - cd.vy) / (eps * (double)cf.ey))));
+    }
+    if (SRC_KIND == PB_KIND_DOUBLE && cf.status != 2 && cd.status != 2 && cf.slot1 == 0 && cd.slot1 == 0) {
+        atomicMax(maxima + 0, __float_as_uint((float)(fabs((double)cf.wx - cd.wx) / (eps * (double)cf.fx_))));
+        atomicMax(maxima + 1, __float_as_uint((float)(fabs((double)cf.wy - cd.wy) / (eps * (double)cf.fy_))));
+    }
+    atomicAdd(counters + 0, 1ULL);
+    if (cf.status != 2 && cd.status != 2 && (cf.status != cd.status || cf.slot1 != cd.slot1)) atomicAdd(counters + 3, 1ULL);
+    Lookup L;
+    if (!fast32_lookup<OUT_KIND, SRC_KIND>(a.out, a.fast.f32, a.src, i, j, L)) {
+        atomicAdd(counters + 1, 1ULL);
+    } else {
+        const Lookup R = resolve_lookup64<OUT_KIND, SRC_KIND>(a.out, a.fast, a.rot, a.src, i, j);
+        if (L.xy0 != R.xy0 || L.xy1 != R.xy1 || !(R.w0 == 1.0 && R.w1 == 1.0)) atomicAdd(counters + 2, 1ULL);
+    }
+}
+
 // get_coordinate_map() + n rotations, materialised.
 template <int OUT_KIND>
 __global__ void __launch_bounds__(256) materialize_map_kernel(const __grid_constant__ OutGeom out,
@@ -415,6 +626,79 @@ __global__ void __launch_bounds__(256) gather_from_map_kernel(const __grid_const
     }
 }
 
+// map_projection (projection.py:550-599), a visualisation of a coordinate map: latitude -> red
+// (stretched over the range it takes on the valid pixels), longitude -> green, invalid -> blue.
+// Pass 1: smallest / largest latitude over the valid pixels (numpy.min / max: a NaN anywhere among
+// them makes the result NaN) and, like the reference, (lat, lon) of the invalid pixels zeroed in
+// place.  Doubles are compared through their order-preserving integer image.
+__device__ __forceinline__ long long ordered_bits(double v) {
+    const long long b = __double_as_longlong(v);
+    return b < 0 ? (long long)(0x8000000000000000ULL - (unsigned long long)b) : b;
+}
+__device__ __forceinline__ double from_ordered_bits(long long o) {
+    return __longlong_as_double(o < 0 ? (long long)(0x8000000000000000ULL - (unsigned long long)o) : o);
+}
+struct MapRange {
+    long long lo, hi;  // ordered_bits of the smallest / largest valid latitude
+    int any_nan, any_valid;
+};
+__global__ void __launch_bounds__(256) map_range_kernel(double* __restrict__ map, long long n, MapRange* __restrict__ range) {
+    long long lo = 0x7fffffffffffffffLL, hi = (long long)0x8000000000000000ULL;
+    int nan = 0, valid = 0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        if (map[p * 3 + 2] != 0.0) {  // projection.py:566: polar_map[invalid_map] = 0 (a view: the caller's map)
+            map[p * 3 + 0] = 0.0;
+            map[p * 3 + 1] = 0.0;
+            continue;
+        }
+        const double lat = map[p * 3];
+        valid = 1;
+        if (lat != lat) nan = 1;
+        else {
+            const long long o = ordered_bits(lat);
+            lo = o < lo ? o : lo;
+            hi = o > hi ? o : hi;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const long long l2 = __shfl_xor_sync(0xffffffffu, lo, off), h2 = __shfl_xor_sync(0xffffffffu, hi, off);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+        nan |= __shfl_xor_sync(0xffffffffu, nan, off);
+        valid |= __shfl_xor_sync(0xffffffffu, valid, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (valid) {
+            atomicMin(&range->lo, lo);
+            atomicMax(&range->hi, hi);
+            atomicOr(&range->any_valid, 1);
+        }
+        if (nan) atomicOr(&range->any_nan, 1);
+    }
+}
+// numpy's float64 -> uint8 cast on x86-64: truncation to a 32-bit integer, low byte kept
+__device__ __forceinline__ unsigned char cast_u8(double v) {
+    if (!(fabs(v) < 2147483648.0)) return 0;  // NaN / out of range: 0x80000000
+    return (unsigned char)(__double2int_rz(v) & 0xff);
+}
+__global__ void __launch_bounds__(256) map_projection_kernel(const double* __restrict__ map, long long n,
+                                                             const MapRange* __restrict__ range, unsigned char* __restrict__ dst) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double lo = range->any_nan ? nan : from_ordered_bits(range->lo);
+    const double hi = range->any_nan ? nan : from_ordered_bits(range->hi);
+    const double factor = __ddiv_rn(255.0, __dadd_rn(hi, -lo));  // :573-574
+    const bool invalid = map[p * 3 + 2] != 0.0;
+    double red = map[p * 3];
+    if (!invalid) red = __dmul_rn(__dadd_rn(red, -lo), factor);  // :576-577 (two in-place passes: two roundings)
+    const double green = __dmul_rn(255.0 / (kPi * 2), map[p * 3 + 1]);  // :583-584
+    dst[p * 3 + 0] = cast_u8(rint(red));    // numpy.round: half to even
+    dst[p * 3 + 1] = cast_u8(rint(green));
+    dst[p * 3 + 2] = invalid ? 255 : 0;
+}
+
 // ------------------------------------------------------------------------------------ launchers
 
 template <int OUT_KIND, int SRC_KIND>
@@ -447,8 +731,37 @@ static void launch_direct_s(const RemapArgs& a, dim3 grid, cudaStream_t st) {
     }
 }
 
+template <int OUT_KIND>
+static void launch_direct32_s(const RemapArgs& a, dim3 grid, cudaStream_t st) {
+    if (a.src.kind == PB_KIND_CAMERA) remap_direct32_kernel<OUT_KIND, PB_KIND_CAMERA><<<grid, 256, 0, st>>>(a);
+    else remap_direct32_kernel<OUT_KIND, PB_KIND_EQUIRECT><<<grid, 256, 0, st>>>(a);
+    PB_COUNT_LAUNCH();
+}
+
+template <int OUT_KIND>
+static void launch_stats_s(const RemapArgs& a, const Fast32GeomT<double>& gd, unsigned* maxima, unsigned long long* counters,
+                           cudaStream_t st) {
+    dim3 block(32, 8);
+    dim3 grid((a.out.W + 31) / 32, (a.out.H + 7) / 8);
+    switch (a.src.kind) {
+        case PB_KIND_CAMERA: fast32_stats_kernel<OUT_KIND, PB_KIND_CAMERA><<<grid, block, 0, st>>>(a, gd, maxima, counters); break;
+        case PB_KIND_DOUBLE: fast32_stats_kernel<OUT_KIND, PB_KIND_DOUBLE><<<grid, block, 0, st>>>(a, gd, maxima, counters); break;
+        default: fast32_stats_kernel<OUT_KIND, PB_KIND_EQUIRECT><<<grid, block, 0, st>>>(a, gd, maxima, counters); break;
+    }
+    PB_COUNT_LAUNCH();
+}
+
 static void launch_direct(const RemapArgs& a, cudaStream_t st) {
     dim3 grid((a.out.W + kTileW - 1) / kTileW, (a.row_end - a.row_begin + kTileH - 1) / kTileH);
+    static const bool compact_off = std::getenv("PB_COMPACT") && std::atoi(std::getenv("PB_COMPACT")) == 0;  // experiments
+    if (a.src.kind != PB_KIND_DOUBLE && a.fast.f32.enabled && !compact_off) {
+        switch (a.out.kind) {
+            case PB_KIND_CAMERA: launch_direct32_s<PB_KIND_CAMERA>(a, grid, st); break;
+            case PB_KIND_DOUBLE: launch_direct32_s<PB_KIND_DOUBLE>(a, grid, st); break;
+            default: launch_direct32_s<PB_KIND_EQUIRECT>(a, grid, st); break;
+        }
+        return;
+    }
     switch (a.out.kind) {
         case PB_KIND_CAMERA: launch_direct_s<PB_KIND_CAMERA>(a, grid, st); break;
         case PB_KIND_DOUBLE: launch_direct_s<PB_KIND_DOUBLE>(a, grid, st); break;
@@ -559,6 +872,25 @@ static cudaError_t launch_tiled(const TiledArgs& a, bool separable, cudaStream_t
     }
 }
 
+// batches with the source staged as a chunk list (pb_chunk.cuh)
+template <int SRC_KIND, int CLS>
+static cudaError_t launch_chunk_one(const TiledArgs& a, cudaStream_t st) {
+    const int smem = chunk_smem_bytes(a.stage_bytes);
+    static int max_smem_set[kMaxDevices] = {0};
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev)) return e;
+    if (dev < 0 || dev >= kMaxDevices || smem > max_smem_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(remap_chunk_kernel<SRC_KIND, CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < kMaxDevices) max_smem_set[dev] = smem;
+    }
+    const int grid = a.tile_list ? a.n_list : a.tiles_x * a.tiles_y;
+    if (grid <= 0) return cudaSuccess;
+    remap_chunk_kernel<SRC_KIND, CLS><<<grid, kTileThreads, smem, st>>>(a);
+    PB_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
 // tuning experiments
 static int env_int(const char* name, int fallback) {
     const char* e = std::getenv(name);
@@ -613,6 +945,7 @@ struct pb_plan {
     int max_units;       // widest staged row of any tile, in 16-byte units (one tensor map per width)
     int raster_band;     // tile rows per raster band (see remap_tiled_kernel)
     int sep1_cap;        // single-frame separable kernel: bytes per stage buffer
+    double* luts;        // device: lens tables of PB_LENS_TABLE lenses (out.lut / src.lut point into it); null otherwise
     double* tables;      // device: col_tab [W][2], row_tab [H][4], then the per-tile footprints; null unless separable
     // separable double-fisheye source: the tiles sorted into two classes, each in raster order --
     // [0, n_one): exactly one lens visible at unit weights, [n_one, n_one + n_rest): the rest
@@ -682,6 +1015,7 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     p.rot.n = d.n_rotations;
     std::memcpy(p.rot.m, d.rotations, sizeof(p.rot.m));
     p.fast = derive_fast(d.out, p.out, d.src, p.src, d.n_rotations, d.rotations);
+    p.fast.f32 = fast32_to_float(derive_fast32(p.out, p.src, p.fast));
     p.separable = d.out.kind == PB_KIND_EQUIRECT && d.n_rotations == 0 && d.src.kind != PB_KIND_EQUIRECT &&
                   d.channels == 3;
     p.stage_bytes = 24 * 1024;  // un-tuned default (pb_remap_u8 without a plan)
@@ -689,6 +1023,7 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     p.raster_band = 16;
     p.sep1_cap = (d.src.kind == PB_KIND_DOUBLE ? 48 : 24) * 1024;  // un-tuned default
     if (const char* e = std::getenv("PB_RASTER_BAND")) p.raster_band = std::atoi(e);  // tuning experiments
+    p.luts = nullptr;
     p.tables = nullptr;
     p.tile_lists = nullptr;
     p.n_one = p.n_rest = 0;
@@ -1131,6 +1466,9 @@ static int plan_run(pb_plan& p, const double* tables, const uint8_t* src, int64_
         // (8K target) or harmful (double source, -8 %), so it is off  (gpurun_out/run3.log, run12.log)
         a.l2_ahead = 0;
         if (const char* e = std::getenv("PB_L2_AHEAD")) a.l2_ahead = std::atoi(e);  // tuning experiments
+        // source rectangles are re-read by neighbouring tiles (keep them), output tiles are written once
+        a.load_policy = env_int("PB_LOAD_POLICY", 0);
+        a.store_policy = env_int("PB_STORE_POLICY", 2);
         a.lean_min_groups = 1;
         if (const char* e = std::getenv("PB_LEAN_MIN_GROUPS")) a.lean_min_groups = std::atoi(e);  // tuning experiments
 #ifdef PB_EXPERIMENTS
@@ -1205,10 +1543,32 @@ static int plan_run(pb_plan& p, const double* tables, const uint8_t* src, int64_
                 b.tile_list = p.tile_lists;
                 b.n_list = p.n_one;
                 b.stage_bytes = env_int("PB_ONE_BYTES", 21 * 1024);  // four CTAs per SM
-                e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 2>(a, lane ? lane->side : st);
-                if (e == cudaSuccess) e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 1>(b, st);
+                // the two-lens / blend-band tiles stage the chunks their pixels touch instead of bounding
+                // rectangles (pb_chunk.cuh); PB_CHUNK: bit 0 = that class, bit 1 = the one-lens class too
+                const int chunk = env_int("PB_CHUNK", 0);
+                const int skip = env_int("PB_SKIP_CLASS", 0);  // timing experiments: leave one grid out (wrong output)
+                if (skip == 2) {
+                    e = cudaSuccess;
+                } else if (chunk & 1) {
+                    a.stage_bytes = env_int("PB_CHUNK_REST_KIB", 94) * 1024;
+                    e = launch_chunk_one<PB_KIND_DOUBLE, 2>(a, lane ? lane->side : st);
+                } else {
+                    e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 2>(a, lane ? lane->side : st);
+                }
+                if (e == cudaSuccess && skip != 1) {
+                    if (chunk & 2) {
+                        b.stage_bytes = env_int("PB_CHUNK_ONE_KIB", 38) * 1024;
+                        e = launch_chunk_one<PB_KIND_DOUBLE, 1>(b, st);
+                    } else {
+                        e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 1>(b, st);
+                    }
+                }
                 const cudaError_t ej = join_side(lane, st);  // always: st must not run ahead of the side grid
                 if (e == cudaSuccess) e = ej;
+            }
+            else if (sep && whole && multi && !dbl && (env_int("PB_CHUNK", 0) & 4)) {
+                a.stage_bytes = env_int("PB_CHUNK_CAM_KIB", 38) * 1024;
+                e = launch_chunk_one<PB_KIND_CAMERA, 0>(a, st);
             }
             else
                 e = launch_tiled(a, sep, st);
@@ -1266,6 +1626,8 @@ int pb_remap_u8(const pb_remap_desc* desc, const uint8_t* src, int64_t src_frame
     // no footprint census without a plan: the single-frame tables mark every rectangle of up to
     // kMaxStageUnits units as staged, so a tensor map must exist for every width
     p.max_units = kMaxStageUnits;
+    if (cudaError_t e = upload_lens_tables(&desc->out, &p.out, &desc->src, &p.src, &p.luts, st, true))
+        return cuda_fail(e, "pb_remap_u8 lens tables");
     double* tables = nullptr;
     if (p.separable) {
         // transient, stream-ordered: nothing outlives the call
@@ -1274,11 +1636,13 @@ int pb_remap_u8(const pb_remap_desc* desc, const uint8_t* src, int64_t src_frame
             tables = nullptr;  // no memory pool on this device: the generic rays need no tables
         } else if (cudaError_t e = fill_tables(p, tables, st)) {
             cudaFreeAsync(tables, st);
+            if (p.luts) cudaFreeAsync(p.luts, st);
             return cuda_fail(e, "pb_remap_u8 tables launch");
         }
     }
     const int rc = plan_run(p, tables, src, src_frame_stride, dst, dst_frame_stride, n_frames, st);
     if (tables) cudaFreeAsync(tables, st);
+    if (p.luts) cudaFreeAsync(p.luts, st);
     return rc;
 }
 
@@ -1294,11 +1658,18 @@ int pb_plan_create(const pb_remap_desc* desc, void* stream, pb_plan** plan_out) 
         delete p;
         return cuda_fail(e, "pb_plan_create");
     }
+    e = upload_lens_tables(&desc->out, &p->out, &desc->src, &p->src, &p->luts, (cudaStream_t)stream, false);
+    if (e != cudaSuccess) {
+        delete p;
+        return cuda_fail(e, "pb_plan_create lens tables");
+    }
+    p->desc.out.lens_table = p->desc.src.lens_table = nullptr;  // the host tables are the caller's
     if (p->separable) {
         e = cudaMalloc((void**)&p->tables, table_doubles(*p) * sizeof(double));
         if (e == cudaSuccess) e = fill_tables(*p, p->tables, (cudaStream_t)stream);
         if (e != cudaSuccess) {
             if (p->tables) cudaFree(p->tables);
+            if (p->luts) cudaFree(p->luts);
             delete p;
             return cuda_fail(e, "pb_plan_create tables");
         }
@@ -1336,6 +1707,7 @@ int pb_plan_remap_rows_u8(const pb_plan* plan, const uint8_t* src, uint8_t* dst_
 void pb_plan_destroy(pb_plan* plan) {
     if (!plan) return;
     if (plan->tables) cudaFree(plan->tables);
+    if (plan->luts) cudaFree(plan->luts);
     if (plan->tile_lists) cudaFree(plan->tile_lists);
     if (plan->sep1_cls) cudaFree(plan->sep1_cls);
     for (int k = 0; k < plan->n_lanes; ++k) {
@@ -1359,13 +1731,79 @@ int pb_materialize_map_f64(const pb_remap_desc* desc, double* map, void* stream)
     dim3 block(32, 8);
     dim3 grid((g.W + block.x - 1) / block.x, (g.H + block.y - 1) / block.y);
     cudaStream_t st = (cudaStream_t)stream;
+    double* luts = nullptr;
+    if (cudaError_t eu = upload_lens_tables(&desc->out, &g, nullptr, nullptr, &luts, st, true))
+        return cuda_fail(eu, "pb_materialize_map_f64 lens table");
     switch (g.kind) {
         case PB_KIND_CAMERA: materialize_map_kernel<PB_KIND_CAMERA><<<grid, block, 0, st>>>(g, rot, map); PB_COUNT_LAUNCH(); break;
         case PB_KIND_DOUBLE: materialize_map_kernel<PB_KIND_DOUBLE><<<grid, block, 0, st>>>(g, rot, map); PB_COUNT_LAUNCH(); break;
         default: materialize_map_kernel<PB_KIND_EQUIRECT><<<grid, block, 0, st>>>(g, rot, map); PB_COUNT_LAUNCH(); break;
     }
     cudaError_t e = cudaGetLastError();
+    if (luts) cudaFreeAsync(luts, st);
     if (e != cudaSuccess) return cuda_fail(e, "pb_materialize_map_f64 launch");
+    return PB_OK;
+}
+
+int pb_map_projection_u8(double* map, int32_t map_height, int32_t map_width, uint8_t* dst, void* stream) {
+    if (!map || !dst) return fail(PB_ERR_INVALID_ARGUMENT, "pb_map_projection_u8: null pointer");
+    if (map_height < 0 || map_width < 0) return fail(PB_ERR_INVALID_ARGUMENT, "pb_map_projection_u8: negative map size");
+    const long long n = (long long)map_height * map_width;
+    if (n == 0) return PB_OK;
+    if ((n + 255) / 256 > 0x7fffffffLL) return fail(PB_ERR_UNSUPPORTED, "pb_map_projection_u8: map too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    MapRange* range = nullptr;  // transient, stream-ordered: nothing outlives the call
+    cudaError_t e = cudaMallocAsync((void**)&range, sizeof(MapRange), st);
+    if (e != cudaSuccess) return cuda_fail(e, "pb_map_projection_u8");
+    const MapRange init = {0x7fffffffffffffffLL, (long long)0x8000000000000000ULL, 0, 0};
+    e = cudaMemcpyAsync(range, &init, sizeof(init), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 148 * 16);
+        map_range_kernel<<<blocks, 256, 0, st>>>(map, n, range);
+        PB_COUNT_LAUNCH();
+        map_projection_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(map, n, range, dst);
+        PB_COUNT_LAUNCH();
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(range, st);
+    if (e != cudaSuccess) return cuda_fail(e, "pb_map_projection_u8 launch");
+    return PB_OK;
+}
+
+int pb_debug_fast32_stats(const pb_remap_desc* desc, double stats[6], void* stream) {
+    if (!stats) return fail(PB_ERR_INVALID_ARGUMENT, "pb_debug_fast32_stats: null pointer");
+    if (int rc = validate_desc(desc, "pb_debug_fast32_stats")) return rc;
+    pb_plan p;
+    plan_init(p, *desc);
+    const Fast32GeomT<double> gd = derive_fast32(p.out, p.src, p.fast);
+    RemapArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.out = p.out;
+    a.src = p.src;
+    a.rot = p.rot;
+    a.fast = p.fast;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* dev = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dev, 8 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return cuda_fail(e, "pb_debug_fast32_stats");
+    cudaMemsetAsync(dev, 0, 8 * sizeof(unsigned long long), st);
+    unsigned* maxima = reinterpret_cast<unsigned*>(dev + 4);
+    switch (a.out.kind) {
+        case PB_KIND_CAMERA: launch_stats_s<PB_KIND_CAMERA>(a, gd, maxima, dev, st); break;
+        case PB_KIND_DOUBLE: launch_stats_s<PB_KIND_DOUBLE>(a, gd, maxima, dev, st); break;
+        default: launch_stats_s<PB_KIND_EQUIRECT>(a, gd, maxima, dev, st); break;
+    }
+    unsigned long long host[8];
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (e != cudaSuccess) return cuda_fail(e, "pb_debug_fast32_stats");
+    float mx[2];
+    std::memcpy(mx, host + 4, sizeof(mx));
+    stats[0] = mx[0];
+    stats[1] = mx[1];
+    for (int k = 0; k < 4; ++k) stats[2 + k] = (double)host[k];
     return PB_OK;
 }
 
@@ -1400,12 +1838,16 @@ int pb_gather_from_map_u8(const pb_image_desc* src_desc, int32_t channels, doubl
     if ((n + 255) / 256 > 0x7fffffffLL) return fail(PB_ERR_UNSUPPORTED, "pb_gather_from_map_u8: map too large");
     SrcGeom s = derive_src(*src_desc, channels);
     cudaStream_t st = (cudaStream_t)stream;
+    double* luts = nullptr;
+    if (cudaError_t eu = upload_lens_tables(nullptr, nullptr, src_desc, &s, &luts, st, true))
+        return cuda_fail(eu, "pb_gather_from_map_u8 lens table");
     switch (s.kind) {
         case PB_KIND_CAMERA: launch_gather_c<PB_KIND_CAMERA>(s, map, n, src, dst, st); break;
         case PB_KIND_DOUBLE: launch_gather_c<PB_KIND_DOUBLE>(s, map, n, src, dst, st); break;
         default: launch_gather_c<PB_KIND_EQUIRECT>(s, map, n, src, dst, st); break;
     }
     cudaError_t e = cudaGetLastError();
+    if (luts) cudaFreeAsync(luts, st);
     if (e != cudaSuccess) return cuda_fail(e, "pb_gather_from_map_u8 launch");
     return PB_OK;
 }

@@ -36,7 +36,7 @@
 #include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through the runtime)
 
 #include "pb_device.cuh"
-#include "pb_fast.cuh"
+#include "pb_fast32.cuh"
 #include "pb_ptx.cuh"
 
 namespace pb {
@@ -83,6 +83,7 @@ struct TiledArgs {
     int lean_min_groups;  // tiles that cannot keep this many frames in flight use the (frame, slot) item loop
     int l2_ahead;     // items whose boxes are prefetched into L2 ahead of the shared-memory loads
     int raster_band;  // CTAs walk bands of this many tile rows column by column (0: plain row-major)
+    int load_policy, store_policy;  // L2 eviction priority of the staged source / the stored tiles (ptx::policy_of)
 #ifdef PB_EXPERIMENTS
     int debug;  // timing experiments (wrong output): 1 = no loads / waits, 2 = no gather, 4 = no stores
 #endif
@@ -127,12 +128,12 @@ __global__ void __launch_bounds__(256) pb_tables_kernel(const __grid_constant__ 
         double* r = row_tab + 4 * t;
         if (src.kind == PB_KIND_DOUBLE) {
             const double lat_r = __dadd_rn(__dmul_rn(lat, -1.0), kPi);
-            r[0] = __dmul_rn(lens_forward(src.lens, lat, src.rect_limit), src.f);
-            r[1] = __dmul_rn(lens_forward(src.lens, lat_r, src.rect_limit), src.f);
+            r[0] = __dmul_rn(lens_forward(src, lat), src.f);
+            r[1] = __dmul_rn(lens_forward(src, lat_r), src.f);
             r[2] = merge_weight(src, lat);
             r[3] = merge_weight(src, lat_r);
         } else {
-            r[0] = __dmul_rn(lens_forward(src.lens, lat, src.rect_limit), src.f);
+            r[0] = __dmul_rn(lens_forward(src, lat), src.f);
             r[1] = 0.0;
             r[2] = 1.0;
             r[3] = 1.0;
@@ -671,7 +672,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     // (separable double source: tiles of the blend band run it too, with the per-row weighted blend)
     // (the lean loop only needs one frame's rectangles to fit the whole stage area)
     const bool lean = (unit_weights || (MODE == 1 && DBL && !ONE)) && n_act >= 1 && n_groups >= a.lean_min_groups &&
-                      !wide && (a.n_out == 2 || a.n_frames == 1) && !dbg_noload && !dbg_nogather && !dbg_nostore;
+                      !wide && (a.n_out == 2 || a.n_frames == 1);  // (the timing experiments apply to either loop)
     if (!staged && !lean) {  // block-uniform
         direct_tile<OUT_KIND, SRC_KIND, MODE>(a, xy_scratch, w_scratch, out_tiles, x0, y0);
         return;
@@ -679,7 +680,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     auto issue_group = [&](int f, int g) {  // one thread: every rectangle of frame f into group g
         unsigned char* base = stages + g * group_bytes + 128;
         ptx::mbarrier_arrive_expect_tx(&sh->bar[g], (unsigned)(rect0 + rect1));
-        const uint64_t keep = ptx::policy_evict_last();
+        const uint64_t keep = ptx::policy_of(a.load_policy);
         if (nbox[0] > 0) {
             const CUtensorMap* map = &a.src_maps[(pitch[0] >> 5) - (kMinStageUnits >> 1)];
             for (int k = 0; k < nbox[0]; ++k)
@@ -702,7 +703,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     };
     if (lean) {
         if (tid < n_groups * 8) reinterpret_cast<int4*>(stages + (tid >> 3) * group_bytes)[tid & 7] = make_int4(0, 0, 0, 0);
-        if (tid == 0) {
+        if (tid == 0 && !dbg_noload) {
             for (int f = 0; f < n_groups; ++f) issue_group(f, f);
             for (int f = n_groups; f < min(n_groups + a.l2_ahead, a.n_frames); ++f) prefetch_group(f);
         }
@@ -769,7 +770,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
     // barrier; thread 0 refills the group and stores the tile right after it.
     const unsigned stages_sa = ptx::smem_addr(stages);
     if (lean) {
-        const uint64_t drop = ptx::policy_evict_first();
+        const uint64_t drop = ptx::policy_of(a.store_policy);
         const unsigned out_sa = ptx::smem_addr(out_tiles) + rg * kOutRowBytes + qc * 12;
         const unsigned out_flip = (a.n_out == 2) ? kOutTileBytes : 0;
         const unsigned bar_sa = ptx::smem_addr(&sh->bar[0]);
@@ -803,9 +804,12 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
             unsigned parity = 0;
             for (int f = 0; f < a.n_frames; ++f) {
                 const unsigned goff = (unsigned)(g * group_bytes);
-                ptx::mbarrier_wait_sa(bar_sa + 8 * g, parity);
+                if (!dbg_noload) ptx::mbarrier_wait_sa(bar_sa + 8 * g, parity);
                 unsigned v[kPxPerThread];
-                if (wgt) {
+                if (dbg_nogather) {
+#pragma unroll
+                    for (int p = 0; p < kPxPerThread; ++p) v[p] = adr[0][p] + f;
+                } else if (wgt) {
                     unsigned w[kPxPerThread];
 #pragma unroll
                     for (int p = 0; p < kPxPerThread; ++p) {
@@ -848,8 +852,8 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                 if (tid == 0) ptx::bulk_wait_read0();  // stores up to frame f - 1 have left their tiles
                 __syncthreads();
                 if (tid == 0) {
-                    if (f + n_groups < a.n_frames) issue_group(f + n_groups, g);
-                    ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, ys, f, out_tiles + (f & 1) * out_flip, drop);
+                    if (f + n_groups < a.n_frames && !dbg_noload) issue_group(f + n_groups, g);
+                    if (!dbg_nostore) ptx::tma_store_3d_hint(&a.dst_map, x0 * 3, ys, f, out_tiles + (f & 1) * out_flip, drop);
                     ptx::bulk_commit();
                     if (a.l2_ahead > 0 && f + n_groups + a.l2_ahead < a.n_frames) prefetch_group(f + n_groups + a.l2_ahead);
                 }

@@ -29,6 +29,10 @@ class ImageGeometry:
     lens: int = 0
     fov: float = 0.0
     f_distance: float = 0.0
+    # LENS_TABLE (a user-defined Lens): float64 samples of the one lens function this side of the
+    # remap evaluates, on [0, table_max] (see include/pb_remap.h: pb_image_desc.lens_table)
+    table: Optional[np.ndarray] = field(default=None, compare=False)
+    table_max: float = 0.0
 
     @property
     def output_width(self) -> int:
@@ -38,6 +42,19 @@ class ImageGeometry:
     def fill(self, d: _native.ImageDesc) -> None:
         d.kind, d.lens, d.height, d.width = self.kind, self.lens, self.height, self.width
         d.fov, d.f_distance = float(self.fov), float(self.f_distance)
+        if self.lens == _native.LENS_TABLE and self.kind != _native.KIND_EQUIRECT:
+            if self.table is None:
+                raise ValueError("a LENS_TABLE geometry needs its table")
+            d.lens_table = self.table.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # (self keeps it alive)
+            d.lens_table_n = int(self.table.size)
+            d.lens_table_max = float(self.table_max)
+
+    def table_digest(self) -> bytes:
+        if self.table is None:
+            return b""
+        import hashlib
+
+        return hashlib.sha1(self.table.tobytes()).digest()
 
 
 @dataclass(frozen=True)
@@ -76,6 +93,8 @@ def _remap_desc(rays: RayPlan, src: ImageGeometry, channels: int) -> _native.Rem
     d = _native.RemapDesc()
     rays.out.fill(d.out)
     src.fill(d.src)
+    d._keep = (rays.out.table, src.table)       # the host tables must outlive the descriptor
+    d._tables = rays.out.table_digest() + src.table_digest()
     d.channels = channels
     d.n_rotations = len(rays.rotations)
     for k, m in enumerate(rays.rotations):
@@ -85,6 +104,17 @@ def _remap_desc(rays: RayPlan, src: ImageGeometry, channels: int) -> _native.Rem
 
 
 # ----------------------------------------------------------------------------- plans
+
+
+def _desc_key(desc: _native.RemapDesc) -> bytes:
+    """Identity of a remap for the plan cache: the descriptor's bytes with the host pointers of
+    lens tables replaced by a digest of what they point at."""
+    tables = getattr(desc, "_tables", b"")
+    if not tables:
+        return bytes(desc)
+    clone = _native.RemapDesc.from_buffer_copy(bytes(desc))
+    clone.out.lens_table = clone.src.lens_table = None
+    return bytes(clone) + tables
 
 
 class _PlanCache:
@@ -101,7 +131,7 @@ class _PlanCache:
         self._lock = threading.RLock()
 
     def get(self, lib, desc: _native.RemapDesc, device_index: int, torch) -> ctypes.c_void_p:
-        key = (device_index, bytes(desc))
+        key = (device_index, _desc_key(desc))
         with self._lock:
             handle = self._plans.pop(key, None)
             if handle is None:
@@ -319,4 +349,25 @@ def gather_from_map_device(src: ImageGeometry, cmap_dev, src_dev, out_dev=None):
             ctypes.byref(d), ctypes.c_int32(c), ctypes.c_void_p(cmap_dev.data_ptr()),
             ctypes.c_int32(mh), ctypes.c_int32(mw), ctypes.c_void_p(src_dev.data_ptr()),
             ctypes.c_void_p(out_dev.data_ptr()), _stream_ptr(torch)))
+    return out_dev
+
+
+def map_projection_device(cmap_dev, out_dev=None):
+    """map_projection (reference projection.py:550-599) of a float64 CUDA map (H, W, 3): uint8 CUDA
+    image (H, W, 3); zeroes (lat, lon) of the invalid entries of ``cmap_dev`` in place like the reference."""
+    torch = _torch()
+    lib = _native.load()
+    if cmap_dev.dim() != 3 or cmap_dev.shape[2] != 3 or cmap_dev.dtype != torch.float64 or not cmap_dev.is_cuda:
+        raise ValueError("coordinate map must be a float64 CUDA tensor of shape (H, W, 3)")
+    if not cmap_dev.is_contiguous():
+        raise ValueError("coordinate map must be contiguous")
+    mh, mw = cmap_dev.shape[0], cmap_dev.shape[1]
+    if out_dev is None:
+        out_dev = torch.empty((mh, mw, 3), dtype=torch.uint8, device=cmap_dev.device)
+    elif (tuple(out_dev.shape) != (mh, mw, 3) or out_dev.dtype != torch.uint8 or not out_dev.is_contiguous()
+          or out_dev.device != cmap_dev.device):
+        raise ValueError(f"out must be a contiguous uint8 tensor of shape {(mh, mw, 3)} on {cmap_dev.device}")
+    with torch.cuda.device(cmap_dev.device):
+        _native.check(lib.pb_map_projection_u8(ctypes.c_void_p(cmap_dev.data_ptr()), ctypes.c_int32(mh), ctypes.c_int32(mw),
+                                               ctypes.c_void_p(out_dev.data_ptr()), _stream_ptr(torch)))
     return out_dev

@@ -15,6 +15,11 @@ Same command names, arguments, options and exit behaviour as the reference
   the reference does (alter_photo.py:142) -- harmless when both have the same shape, and
   reproduced as is otherwise.
 
+A DIRECTORY as INPUT (an extension over the reference: the frames of a video, photos from one
+camera) converts every .jpg/.jpeg/.png in it with the same parameters into the OUTPUT directory,
+frames sharded over the visible GPUs (photonbend_b200/stream.py); ``--frames-per-launch`` sets how
+many frames share a kernel launch.
+
 Everything between decode and encode runs on the GPU: the source array is uploaded once, the
 three-call protocol (get_coordinate_map / rotate_coordinate_map / process_coordinate_map) costs
 one kernel launch, and the result is downloaded once.
@@ -136,6 +141,58 @@ def _remap(source, destination, rotations: List[Tuple[float, float, float]]) -> 
     return source.process_coordinate_map(coordinate_map)
 
 
+def _remap_directory(in_dir: Path, out_dir: Path, make_pair, rotations, frames_per_launch: int) -> None:
+    """Every image of ``in_dir`` through the geometry ``make_pair(first_frame_pixels)`` ->
+    (source, destination) into ``out_dir`` (same file names), sharded over the visible GPUs."""
+    from photonbend_b200 import stream
+
+    out_dir = Path(out_dir)
+    if out_dir.suffix.lower() in (".jpg", ".jpeg", ".png") or (out_dir.exists() and not out_dir.is_dir()):
+        print("The input is a directory of frames: the output must be a directory too.")
+        print("Exiting!")
+        sys.exit(1)
+    files = stream.list_frames(in_dir)
+    if not files:
+        print("Error: no .jpg / .jpeg / .png frames in the input directory!")
+        print("Exiting!")
+        sys.exit(1)
+    outs = [out_dir / f.name for f in files]
+    if any(o.exists() for o in outs):
+        answer = ""
+        while answer not in ("y", "n"):
+            answer = input("Output frames already exist. Overwrite? (y/n) ")
+        if answer == "n":
+            print("Exiting!")
+            sys.exit(0)
+    try:
+        out_dir.mkdir(parents=True, exist_ok=True)
+    except OSError:
+        print("Could not save to the specified location!")
+        print("Exiting!")
+        sys.exit(1)
+    first = _load_pixels(files[0])
+    if not isinstance(first, np.ndarray):
+        first = first.cpu().numpy()
+    source, destination = make_pair(first)
+    coordinate_map = destination.get_coordinate_map()
+    for pitch, yaw, roll in rotations:
+        coordinate_map = Rotation(to_radians(pitch), to_radians(yaw), to_radians(roll)).rotate_coordinate_map(
+            coordinate_map)
+    try:
+        stats = stream.remap_files(source, coordinate_map, files, outs, batch=max(1, frames_per_launch))
+    except IOError:
+        print("Could not read or save a frame!")
+        print("Exiting!")
+        sys.exit(1)
+    print(f"{stats['frames']} frames on {stats['gpus']} GPU(s) in {stats['seconds']:.2f} s "
+          f"({stats['kernel_launches']} launches, codec {stats['codec']})")
+
+
+def _frames_option(fn):
+    return click.option("--frames-per-launch", required=False, type=click.INT, default=4,
+                        help="Directory input only: frames remapped by one kernel launch.")(fn)
+
+
 def _rotation_option(fn):
     return click.option("-r", "--rotation", required=False, type=click.FLOAT, nargs=3, default=[],
                         help=_ROTATION_HELP, multiple=True)(fn)
@@ -159,19 +216,24 @@ def _size_option(fn):
               help="The lens field of view of the input photo in degrees. " + _DOUBLE_FOV_NOTE)
 @_rotation_option
 @_size_option
+@_frames_option
 @click.argument("output_image", type=click.Path(exists=False, path_type=Path))
-def make_pano(input_image, itype, lens, fov, output_image, rotation, size):
+def make_pano(input_image, itype, lens, fov, output_image, rotation, size, frames_per_launch):
     """Make a panorama out of a photo.
 
     \b
-    INPUT is the path to the source photo.
-    OUTPUT is the desired path of the destiny panorama.
+    INPUT is the path to the source photo (or a directory of frames).
+    OUTPUT is the desired path of the destiny panorama (a directory for a directory).
     """
+    def pair(pixels):
+        source = _photo(pixels, itype, lens, _fov_radians(fov, itype), _magnitude(itype, pixels.shape))
+        height = pixels.shape[0] if size is None else size
+        return source, PanoramaImage(np.zeros((height, int(height * 2), CHANNELS), np.uint8))
+
+    if Path(input_image).is_dir():
+        return _remap_directory(input_image, output_image, pair, rotation, frames_per_launch)
     out = _checked_output(output_image)
-    pixels = _load_pixels(input_image)
-    source = _photo(pixels, itype, lens, _fov_radians(fov, itype), _magnitude(itype, pixels.shape))
-    height = pixels.shape[0] if size is None else size
-    destination = PanoramaImage(np.zeros((height, int(height * 2), CHANNELS), np.uint8))
+    source, destination = pair(_load_pixels(input_image))
     _save_pixels(_remap(source, destination, rotation), out)
 
 
@@ -194,20 +256,25 @@ def make_pano(input_image, itype, lens, fov, output_image, rotation, size):
               help="The lens field of view of the output photo in degrees. " + _DOUBLE_FOV_NOTE)
 @_rotation_option
 @_size_option
+@_frames_option
 @click.argument("output_image", type=click.Path(exists=False, path_type=Path))
-def alter_photo(input_image, itype, ilens, ifov, otype, olens, ofov, output_image, rotation, size):
+def alter_photo(input_image, itype, ilens, ifov, otype, olens, ofov, output_image, rotation, size, frames_per_launch):
     """Change the the lens and FoV of a photo.
 
     \b
-    INPUT is the path to the source photo.
-    OUTPUT is the desired path of the destiny photo.
+    INPUT is the path to the source photo (or a directory of frames).
+    OUTPUT is the desired path of the destiny photo (a directory for a directory).
     """
+    def pair(pixels):
+        source = _photo(pixels, itype, ilens, _fov_radians(ifov, itype), _magnitude(itype, pixels.shape))
+        canvas = np.zeros(_photo_shape(otype, pixels.shape, size), np.uint8)
+        # output magnitude from the INPUT shape, as the reference does
+        return source, _photo(canvas, otype, olens, _fov_radians(ofov, otype), _magnitude(otype, pixels.shape))
+
+    if Path(input_image).is_dir():
+        return _remap_directory(input_image, output_image, pair, rotation, frames_per_launch)
     out = _checked_output(output_image)
-    pixels = _load_pixels(input_image)
-    source = _photo(pixels, itype, ilens, _fov_radians(ifov, itype), _magnitude(itype, pixels.shape))
-    canvas = np.zeros(_photo_shape(otype, pixels.shape, size), np.uint8)
-    # output magnitude from the INPUT shape, as the reference does
-    destination = _photo(canvas, otype, olens, _fov_radians(ofov, otype), _magnitude(otype, pixels.shape))
+    source, destination = pair(_load_pixels(input_image))
     _save_pixels(_remap(source, destination, rotation), out)
 
 
@@ -224,19 +291,24 @@ def alter_photo(input_image, itype, ilens, ifov, otype, olens, ofov, output_imag
               help="The lens field of view of the output photo in degrees. " + _DOUBLE_FOV_NOTE)
 @_rotation_option
 @_size_option
+@_frames_option
 @click.argument("output_image", type=click.Path(exists=False, path_type=Path))
-def make_photo(input_image, otype, lens, fov, output_image, rotation, size):
+def make_photo(input_image, otype, lens, fov, output_image, rotation, size, frames_per_launch):
     """Make a photo out of a panorama.
 
     \b
-    INPUT is the path to the source panorama.
-    OUTPUT is the desired path of the destiny photo.
+    INPUT is the path to the source panorama (or a directory of frames).
+    OUTPUT is the desired path of the destiny photo (a directory for a directory).
     """
+    def pair(pixels):
+        shape = _photo_shape(otype, pixels.shape, size)
+        return PanoramaImage(pixels), _photo(np.zeros(shape, np.uint8), otype, lens, _fov_radians(fov, otype),
+                                             _magnitude(otype, shape))
+
+    if Path(input_image).is_dir():
+        return _remap_directory(input_image, output_image, pair, rotation, frames_per_launch)
     out = _checked_output(output_image)
-    pixels = _load_pixels(input_image)
-    source = PanoramaImage(pixels)
-    shape = _photo_shape(otype, pixels.shape, size)
-    destination = _photo(np.zeros(shape, np.uint8), otype, lens, _fov_radians(fov, otype), _magnitude(otype, shape))
+    source, destination = pair(_load_pixels(input_image))
     _save_pixels(_remap(source, destination, rotation), out)
 
 

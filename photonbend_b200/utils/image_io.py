@@ -111,6 +111,25 @@ def decode_jpeg_to_device(data: bytes):
     return out
 
 
+def decode_jpeg_into(data: bytes, out) -> None:
+    """JPEG bytes -> the preallocated uint8 CUDA tensor ``out`` (H, W, 3) (a frame of a batch buffer).
+    Raises CodecError when nvJPEG cannot, ValueError when the sizes differ."""
+    from photonbend_b200 import engine
+
+    torch = engine._torch()
+    lib = load_codec()
+    buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data)
+    w, h, n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    _check(lib, lib.pb_io_jpeg_info(buf, len(data), ctypes.byref(w), ctypes.byref(h), ctypes.byref(n)))
+    if tuple(out.shape) != (h.value, w.value, 3) or out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError(f"decode_jpeg_into: image is {h.value}x{w.value}x3, destination {tuple(out.shape)}")
+    with torch.cuda.device(out.device):
+        stream = torch.cuda.current_stream()
+        _check(lib, lib.pb_io_jpeg_decode_rgb_u8(buf, len(data), ctypes.c_void_p(out.data_ptr()), w.value, h.value,
+                                                 ctypes.c_void_p(stream.cuda_stream)))
+        stream.synchronize()  # `buf` (the host bitstream) must outlive the decode
+
+
 def encode_jpeg_from_device(pixels, quality: int = PILLOW_DEFAULT_QUALITY, subsampling: int = CSS_420) -> bytes:
     """uint8 CUDA tensor (H, W, 3) -> baseline JPEG bytes."""
     from photonbend_b200 import engine
@@ -177,5 +196,5 @@ def save_image(pixels, path, codec: str | None = None) -> None:
     Image.fromarray(np.ascontiguousarray(pixels)).save(path)
 
 
-__all__ = ["open_image", "save_image", "decode_jpeg_to_device", "encode_jpeg_from_device",
+__all__ = ["open_image", "save_image", "decode_jpeg_to_device", "decode_jpeg_into", "encode_jpeg_from_device",
            "selected_codec", "load_codec", "CodecError", "EXPORTS"]

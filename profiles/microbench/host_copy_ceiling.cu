@@ -1,0 +1,100 @@
+// host_copy_ceiling.cu -- what the host of this box can feed: pinned host <-> device copies of
+// 8K frames (88,473,600 bytes, one cfg5 frame) on N GPUs at once, each way alone and both ways
+// together.  This is the ceiling of bench.py's `e2e` figure (every frame crosses PCIe twice); the
+// remap kernel is not involved.
+//
+//   nvcc -O2 -o host_copy_ceiling host_copy_ceiling.cu && ./host_copy_ceiling [n_gpus] [seconds]
+//
+// One JSON line per (n_gpus, mode): aggregate GB/s each way and the Gpix/s of an 8K RGB stream that
+// bandwidth carries (one frame in + one frame out per 29.49 Mpix).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#define CK(x)                                                                                  \
+    do {                                                                                       \
+        cudaError_t e_ = (x);                                                                  \
+        if (e_ != cudaSuccess) {                                                               \
+            std::fprintf(stderr, "%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e_));    \
+            std::exit(1);                                                                      \
+        }                                                                                      \
+    } while (0)
+
+constexpr size_t kFrame = 3840ull * 7680ull * 3ull;
+constexpr int kDepth = 3;  // frames in flight per GPU and direction (the pipeline's depth)
+
+struct Gpu {
+    cudaStream_t up[kDepth], down[kDepth];
+    unsigned char* h_in[kDepth];
+    unsigned char* h_out[kDepth];
+    unsigned char* d_in[kDepth];
+    unsigned char* d_out[kDepth];
+};
+
+static double run(std::vector<Gpu>& gpus, bool h2d, bool d2h, double seconds, long long* frames_each_way) {
+    const int n = (int)gpus.size();
+    long long copies = 0;
+    for (int g = 0; g < n; ++g) {
+        CK(cudaSetDevice(g));
+        CK(cudaDeviceSynchronize());
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    double dt = 0;
+    do {
+        for (int round = 0; round < 4; ++round)
+            for (int g = 0; g < n; ++g) {
+                CK(cudaSetDevice(g));
+                for (int k = 0; k < kDepth; ++k) {
+                    if (h2d) CK(cudaMemcpyAsync(gpus[g].d_in[k], gpus[g].h_in[k], kFrame, cudaMemcpyHostToDevice, gpus[g].up[k]));
+                    if (d2h) CK(cudaMemcpyAsync(gpus[g].h_out[k], gpus[g].d_out[k], kFrame, cudaMemcpyDeviceToHost, gpus[g].down[k]));
+                }
+            }
+        copies += 4 * kDepth;
+        for (int g = 0; g < n; ++g) {
+            CK(cudaSetDevice(g));
+            CK(cudaDeviceSynchronize());
+        }
+        dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    } while (dt < seconds);
+    *frames_each_way = copies * n;
+    return dt;
+}
+
+int main(int argc, char** argv) {
+    int n_dev = 0;
+    CK(cudaGetDeviceCount(&n_dev));
+    int n = argc > 1 ? std::atoi(argv[1]) : n_dev;
+    if (n > n_dev) n = n_dev;
+    const double seconds = argc > 2 ? std::atof(argv[2]) : 2.0;
+    std::vector<Gpu> gpus(n);
+    for (int g = 0; g < n; ++g) {
+        CK(cudaSetDevice(g));
+        for (int k = 0; k < kDepth; ++k) {
+            CK(cudaStreamCreateWithFlags(&gpus[g].up[k], cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&gpus[g].down[k], cudaStreamNonBlocking));
+            CK(cudaHostAlloc((void**)&gpus[g].h_in[k], kFrame, cudaHostAllocDefault));
+            CK(cudaHostAlloc((void**)&gpus[g].h_out[k], kFrame, cudaHostAllocDefault));
+            CK(cudaMalloc((void**)&gpus[g].d_in[k], kFrame));
+            CK(cudaMalloc((void**)&gpus[g].d_out[k], kFrame));
+            for (size_t b = 0; b < kFrame; b += 4096) gpus[g].h_in[k][b] = (unsigned char)b;  // touch the pages
+        }
+    }
+    const char* names[3] = {"h2d", "d2h", "both"};
+    for (int mode = 0; mode < 3; ++mode) {
+        const bool h2d = mode != 1, d2h = mode != 0;
+        long long frames = 0;
+        run(gpus, h2d, d2h, 0.3, &frames);  // warm-up
+        const double dt = run(gpus, h2d, d2h, seconds, &frames);
+        const double gbs = (double)frames * (double)kFrame / dt / 1e9;
+        // an e2e stream needs one frame up and one frame down per output frame
+        const double gpix = (double)frames * 3840.0 * 7680.0 / dt / 1e9;
+        std::printf("{\"n_gpus\": %d, \"mode\": \"%s\", \"GBps_each_way\": %.2f, \"frames_per_s_each_way\": %.1f, "
+                    "\"gpix_per_s_if_stream\": %.2f, \"seconds\": %.2f}\n",
+                    n, names[mode], gbs, frames / dt, mode == 2 ? gpix : 0.0, dt);
+        std::fflush(stdout);
+    }
+    return 0;
+}

@@ -29,15 +29,16 @@ def test_library_exports_every_declared_symbol():
     lib = _native.load()
     for name in _declared_functions():
         assert hasattr(lib, name), name
-    assert lib.pb_version() == 1
+    assert lib.pb_version() == _native.PB_ABI_VERSION == 2
 
 
 def test_struct_layout_matches_header():
     from photonbend_b200 import _native
 
-    assert ctypes.sizeof(_native.ImageDesc) == 32
-    assert ctypes.sizeof(_native.RemapDesc) == 2 * 32 + 8 + _native.PB_MAX_ROTATIONS * 9 * 8
-    assert _native.RemapDesc.rotations.offset == 72
+    assert ctypes.sizeof(_native.ImageDesc) == 56  # 4 x int32, 2 x double, pointer, 2 x int32, double
+    assert _native.ImageDesc.lens_table.offset == 32 and _native.ImageDesc.lens_table_max.offset == 48
+    assert ctypes.sizeof(_native.RemapDesc) == 2 * 56 + 8 + _native.PB_MAX_ROTATIONS * 9 * 8
+    assert _native.RemapDesc.rotations.offset == 120
 
 
 def test_argument_errors_need_no_gpu():

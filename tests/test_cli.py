@@ -87,3 +87,77 @@ def test_make_pano_and_make_photo_match_oracle(tmp_path):
            "magnitude": float(np.sqrt(199.5**2 + 199.5**2))}
     want2 = numpy_port.remap(og2, [(to_radians(-90), 0.0, to_radians(195))], {"kind": "equirect", "height": 512, "width": 1024}, got)
     assert np.array_equal(got2, want2)
+
+
+def test_directory_input_needs_a_directory_output(tmp_path):
+    frames = tmp_path / "frames"
+    frames.mkdir()
+    Image.fromarray(np.zeros((8, 8, 3), np.uint8)).save(frames / "a.png")
+    res = CliRunner().invoke(main, ["make-pano", "--type", "inscribed", "--lens", "equidistant", "--fov", "360",
+                                    str(frames), str(tmp_path / "out.png")])
+    assert res.exit_code == 1 and "must be a directory" in res.output
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    res = CliRunner().invoke(main, ["make-pano", "--type", "inscribed", "--lens", "equidistant", "--fov", "360",
+                                    str(empty), str(tmp_path / "out")])
+    assert res.exit_code == 1 and "no .jpg" in res.output
+
+
+@pytest.mark.gpu
+def test_directory_of_frames_matches_oracle(tmp_path, monkeypatch):
+    """A directory as INPUT (photonbend_b200/stream.py: FramePipeline per GPU, frames sharded
+    k mod G): every frame equals the oracle's remap of that frame; the compressed-stream variant
+    (PHOTONBEND_B200_CODEC=nvjpeg: decode, remap and encode on the device) equals what the
+    single-file command gives with the same codec."""
+    from oracle import numpy_port
+    from photonbend_b200.workloads import to_radians
+
+    rng = np.random.default_rng(3)
+    frames = tmp_path / "frames"
+    frames.mkdir()
+    sg = {"kind": "double", "height": 192, "width": 384, "lens": "equidistant", "fov": to_radians(195)}
+    og = {"kind": "equirect", "height": 160, "width": 320}
+    images = []
+    for k in range(7):
+        img = rng.integers(0, 256, (192, 384, 3), dtype=np.uint8)
+        images.append(img)
+        Image.fromarray(img).save(frames / f"f{k:03d}.png")
+    out = tmp_path / "out"
+    res = CliRunner().invoke(main, ["make-pano", "--type", "double", "--lens", "equidistant", "--fov", "195", "-s", "160",
+                                    "--frames-per-launch", "3", str(frames), str(out)])
+    assert res.exit_code == 0, res.output
+    assert "7 frames" in res.output
+    for k in range(7):
+        with Image.open(out / f"f{k:03d}.png") as im:
+            got = np.asarray(im)
+        assert np.array_equal(got, numpy_port.remap(og, (), sg, images[k])), k
+    # rotated, one frame per launch, existing outputs: prompt once
+    res = CliRunner().invoke(main, ["make-pano", "--type", "double", "--lens", "equidistant", "--fov", "195", "-s", "160",
+                                    "-r", "10", "20", "30", "--frames-per-launch", "1", str(frames), str(out)], input="y\n")
+    assert res.exit_code == 0 and "Overwrite" in res.output, res.output
+    rot = [(to_radians(10), to_radians(20), to_radians(30))]
+    for k in (0, 6):
+        with Image.open(out / f"f{k:03d}.png") as im:
+            got = np.asarray(im)
+        want = numpy_port.remap(og, rot, sg, images[k])
+        diff = (got != want).any(axis=2)
+        assert diff.sum() <= 2 and np.abs(got.astype(int) - want.astype(int)).max() <= 1, k  # 1-LSB blend class only
+
+    # compressed stream: JPEG frames, nvJPEG on the device
+    monkeypatch.setenv("PHOTONBEND_B200_CODEC", "nvjpeg")
+    jframes = tmp_path / "jframes"
+    jframes.mkdir()
+    smooth = np.stack(np.meshgrid(np.arange(384), np.arange(192)), axis=2).sum(axis=2)
+    for k in range(3):
+        img = np.stack([(smooth * (k + 1)) % 256, (smooth // 2) % 256, (smooth * 3) % 256], axis=2).astype(np.uint8)
+        Image.fromarray(img).save(jframes / f"j{k}.jpg", quality=92)
+    jout = tmp_path / "jout"
+    res = CliRunner().invoke(main, ["make-pano", "--type", "double", "--lens", "equidistant", "--fov", "195", "-s", "160",
+                                    "--frames-per-launch", "2", str(jframes), str(jout)])
+    assert res.exit_code == 0 and "codec nvjpeg" in res.output, res.output
+    for k in range(3):
+        single = tmp_path / f"single{k}.jpg"
+        res = CliRunner().invoke(main, ["make-pano", "--type", "double", "--lens", "equidistant", "--fov", "195", "-s", "160",
+                                        str(jframes / f"j{k}.jpg"), str(single)])
+        assert res.exit_code == 0, res.output
+        assert (jout / f"j{k}.jpg").read_bytes() == single.read_bytes(), k

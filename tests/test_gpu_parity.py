@@ -211,7 +211,7 @@ def test_c_abi_direct_call(torch_cuda):
     from photonbend_b200 import _native
 
     lib = _native.load()
-    assert lib.pb_version() == 1
+    assert lib.pb_version() == _native.PB_ABI_VERSION
     sg = {"kind": "camera", "height": 64, "width": 64, "lens": "equidistant",
           "fov": case_matrix.rad(360), "magnitude": 31.5}
     og = {"kind": "equirect", "height": 48, "width": 96}
@@ -656,3 +656,140 @@ def test_plan_shared_by_host_threads(torch_cuda):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def fp32_tier_stats(og, rots, sg):
+    """pb_debug_fast32_stats for a geometry: dict(max_ratio_x, max_ratio_y, pixels, undecided, wrong, status_mismatch)."""
+    import ctypes
+
+    from photonbend_b200 import _native, engine
+
+    cmap = helpers.product_map(og, rots)
+    src = helpers.product_image(sg, np.zeros((sg["height"], sg["width"], 3), np.uint8))
+    desc = engine._remap_desc(cmap.rays, src._source_geometry(), 3)
+    stats = (ctypes.c_double * 6)()
+    _native.check(_native.load().pb_debug_fast32_stats(ctypes.byref(desc), stats, None))
+    keys = ("max_ratio_x", "max_ratio_y", "pixels", "undecided", "wrong", "status_mismatch")
+    return dict(zip(keys, [float(v) for v in stats]))
+
+
+FP32_TIER_K = 16.0  # csrc/pb_remap.cu kFast32K
+
+
+def test_fp32_tier_error_bound(torch_cuda):
+    """csrc/pb_fast32.cuh: the FP32-first tier accepts a pixel only if its float coordinate is
+    further than E = K * 2^-24 * shape from every integer.  Over every pixel of every lens pair x
+    {no, one, two} rotations at mid size, a third of the small matrix and the two rotated BASELINE
+    configurations at full size: (1) the float evaluation never strays from the float64 evaluation of
+    the same formulas by more than HALF the bound (max ratio <= K / 2), (2) no pixel tier 1 decides
+    differs from what the float64 tiers give, (3) float and double agree on every fov / no-pixel
+    decision tier 1 takes."""
+    from photonbend_b200 import workloads
+
+    outs, srcs = _mid_size_geometries()
+    rotsets = ((), ((0.3, -0.2, 1.0),), ((case_matrix.rad(-90), 0.0, case_matrix.rad(195)), (0.1, 0.2, 0.3)))
+    worst, n_px, n_und, n_cases = 0.0, 0.0, 0.0, 0
+    geoms = [(og, rots, sg) for og in outs for sg in srcs for rots in rotsets]
+    geoms += [(og, rots, sg) for _, og, rots, sg, _ in CASES[::3]]
+    geoms += [(workloads.WORKLOADS[n]["out"], workloads.WORKLOADS[n]["rotations"], workloads.WORKLOADS[n]["src"])
+              for n in ("cfg2", "cfg3", "cfg1", "cfg4")]
+    for og, rots, sg in geoms:
+        try:
+            st = fp32_tier_stats(og, rots, sg)
+        except ValueError:
+            continue  # a geometry the reference refuses at construction (rectilinear fov)
+        assert st["wrong"] == 0 and st["status_mismatch"] == 0, (og, rots, sg, st)
+        worst = max(worst, st["max_ratio_x"], st["max_ratio_y"])
+        assert max(st["max_ratio_x"], st["max_ratio_y"]) <= FP32_TIER_K / 2, (og, rots, sg, st)
+        n_px += st["pixels"]
+        n_und += st["undecided"]
+        n_cases += 1
+    print(f"FP32 tier: {n_cases} geometries, {n_px:.0f} pixels, largest |float - double| / (2^-24 shape) = {worst:.2f} "
+          f"(bound K = {FP32_TIER_K}), {n_und / n_px:.4f} of the pixels left to the float64 tiers")
+
+
+def test_map_projection_on_device(torch_cuda, golden_small):
+    """core.map_projection (pb_map_projection_u8, reference projection.py:550-599): bit-identical to
+    the live reference's outputs on the reference's own maps (ndarray argument: uploaded, invalid
+    entries zeroed in place like the reference does), and within rounding of them on the map the
+    device materialises itself (CUDA's libm differs from NumPy's in the last ulp, which can move a
+    value across a .5 rounding boundary)."""
+    from photonbend_b200.core import map_projection
+
+    _, _, maps = golden_small
+    golden = np.load(os.path.join(GOLDEN, "map_projection.npz"))
+    geoms = dict(case_matrix.output_geometries())
+    rotsets = dict(case_matrix.ROTATION_SETS)
+    n_px = n_off = 0
+    for key in golden.files:
+        cmap = maps[key].copy()
+        got = map_projection(cmap)
+        assert got.dtype == np.uint8 and np.array_equal(got, golden[key]), key
+        assert np.all(cmap[cmap[:, :, 2] != 0, :2] == 0), key
+        oname, rname = key.split("__")
+        lazy = map_projection(helpers.product_map(geoms[oname], rotsets[rname]))
+        diff = np.abs(lazy.astype(np.int16) - golden[key].astype(np.int16))
+        diff = np.minimum(diff, 256 - diff)  # the green channel wraps (negative longitudes)
+        # the +-pi seam: a longitude of pi - 1e-16 shows as 127, one of -pi + 1e-16 as 129
+        seam = np.isin(lazy[:, :, 1], (127, 128, 129)) & np.isin(golden[key][:, :, 1], (127, 128, 129))
+        diff[:, :, 1][seam] = 0
+        assert diff.max() <= 1, (key, int(diff.max()), int((diff > 1).sum()))
+        n_px += diff[:, :, 0].size
+        n_off += int((diff > 0).any(axis=2).sum())
+    assert n_off <= 2e-3 * n_px, (n_off, n_px)
+    with pytest.raises(ValueError):
+        map_projection(np.ones((4, 4, 3)))  # no valid pixel: numpy.min of an empty selection
+
+
+def test_user_defined_lens_through_tables(torch_cuda):
+    """A Lens built from user callables (reference lens.py:48-64) runs on the GPU through a table of
+    samples (PB_LENS_TABLE, linear interpolation; include/pb_remap.h).  With callables that compute
+    what a built-in model computes, the pixels are those of the built-in model except where the
+    interpolation error (~1e-7 px) moves a coordinate across an integer: at most a handful of
+    pixels, each the neighbouring source pixel.  Fused path (both roles, rotated and not, one frame
+    and a batch) and the explicit-map path."""
+    torch = torch_cuda
+    from photonbend_b200.core.lens import Lens, equisolid, stereographic
+    from photonbend_b200.core.projection import CameraImage, DoubleCameraImage, PanoramaImage
+    from photonbend_b200.core.rotation import Rotation
+
+    pairs = [
+        (equisolid(), Lens(lambda t: 2 * np.sin(t / 2), lambda r: 2 * np.arcsin(r / 2))),
+        (stereographic(), Lens(lambda t: 2 * np.tan(t / 2), lambda r: 2 * np.arctan(r / 2))),
+    ]
+    rng = np.random.default_rng(11)
+    photo = rng.integers(0, 256, (240, 256, 3), dtype=np.uint8)
+    pano = rng.integers(0, 256, (192, 384, 3), dtype=np.uint8)
+    dbl = rng.integers(0, 256, (192, 384, 3), dtype=np.uint8)
+    n_px = n_bad = 0
+    for builtin, custom in pairs:
+        for rot in (None, (0.3, -0.2, 1.0)):
+            results = []
+            for lens in (builtin, custom):
+                outs = []
+                # custom lens as the SOURCE: photo -> panorama, double -> panorama
+                cmap = PanoramaImage(np.zeros((160, 320, 3), np.uint8)).get_coordinate_map()
+                if rot:
+                    cmap = Rotation(*rot).rotate_coordinate_map(cmap)
+                outs.append(CameraImage(photo, case_matrix.rad(200), lens, magnitude=127.5).process_coordinate_map(cmap))
+                outs.append(DoubleCameraImage(dbl, case_matrix.rad(195), lens).process_coordinate_map(cmap))
+                # custom lens as the OUTPUT: panorama -> photo
+                cmap = CameraImage(np.zeros((200, 272, 3), np.uint8), case_matrix.rad(150), lens, magnitude=135.5).get_coordinate_map()
+                if rot:
+                    cmap = Rotation(*rot).rotate_coordinate_map(cmap)
+                outs.append(PanoramaImage(pano).process_coordinate_map(cmap))
+                # explicit map: materialised with the custom reverse function, gathered with the custom forward
+                explicit = np.asarray(cmap).copy()
+                outs.append(CameraImage(photo, case_matrix.rad(200), lens, magnitude=127.5).process_coordinate_map(explicit))
+                # a device batch through the custom source lens
+                batch = torch.from_numpy(np.stack([photo, photo[::-1].copy()])).cuda()
+                cmap = PanoramaImage(np.zeros((160, 320, 3), np.uint8)).get_coordinate_map()
+                outs.append(CameraImage(batch, case_matrix.rad(200), lens, magnitude=127.5).process_coordinate_map(cmap).cpu().numpy())
+                results.append(outs)
+            for a, b in zip(*results):
+                assert a.shape == b.shape
+                diff = (a != b).any(axis=-1)
+                n_px += diff.size
+                n_bad += int(diff.sum())
+    print(f"user-defined lens tables: {n_bad} of {n_px} pixels differ from the built-in model")
+    assert n_bad <= max(4, 2e-5 * n_px), (n_bad, n_px)

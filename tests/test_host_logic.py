@@ -50,12 +50,13 @@ def test_rectilinear_raises_like_reference():
     assert np.isnan(big[1]) and np.isnan(big[2]) and not np.isnan(big[0])
 
 
-def test_custom_lens_is_rejected_not_emulated():
+def test_custom_lens_is_sampled_not_refused():
     custom = Lens(lambda t: t * 1.01, lambda r: r / 1.01)
-    cam = CameraImage(np.zeros((8, 8, 3), np.uint8), 2.0, custom)  # construction works: f is host math
+    cam = CameraImage(np.zeros((8, 8, 3), np.uint8), 2.0, custom)  # construction: f is host math
     assert cam.f_distance == pytest.approx(4.0 / 1.01)
-    with pytest.raises(NotImplementedError):
-        cam.get_coordinate_map()
+    rays = cam.get_coordinate_map().rays  # lazy: no kernel, but the reverse function is sampled
+    assert rays.out.lens == 6 and rays.out.table is not None
+    assert rays.out.table[-1] == pytest.approx(rays.out.table_max / 1.01)
 
 
 def test_focal_distance_and_magnitude_defaults():
@@ -134,3 +135,42 @@ def test_size_helper():
         calculate_size_panorama_to_photo((100, 60), pb_lens.equidistant().forward_function)
     side = calculate_size_panorama_to_photo((2048, 1024), pb_lens.equisolid().forward_function, True)
     assert side[0] == side[1] and side[0] >= 922
+
+
+def test_user_defined_lens_becomes_a_table():
+    """A Lens of user callables (reference lens.py:48-64) is not refused: it is sampled into a
+    table per role (forward on [0, pi] as a source, reverse on [0, largest pixel radius] as an
+    output), the descriptor carries the host pointers, and the plan-cache key carries the tables'
+    content instead of their addresses."""
+    import ctypes
+
+    import numpy as np
+
+    from photonbend_b200 import _native, engine
+    from photonbend_b200.core.lens import LENS_TABLE_SAMPLES, Lens, equisolid, lens_id
+    from photonbend_b200.core.projection import CameraImage
+
+    builtin = equisolid()
+    assert lens_id(builtin.forward_function, builtin.reverse_function) == _native.LENS_EQUISOLID
+    custom = Lens(lambda t: 2 * np.sin(t / 2), lambda r: 2 * np.arcsin(r / 2))
+    assert lens_id(custom.forward_function, custom.reverse_function) == _native.LENS_TABLE
+    cam = CameraImage(np.zeros((64, 80, 3), np.uint8), np.pi * 0.9, custom, magnitude=31.5)
+    src, out = cam._source_geometry(), cam._output_geometry()
+    assert src.table.shape == (LENS_TABLE_SAMPLES,) and src.table_max == np.pi
+    assert np.allclose(src.table[[0, -1]], [0.0, 2.0])
+    assert np.isclose(out.table_max, np.hypot(39.5, 31.5) / cam.f_distance)
+    assert cam._source_geometry().table is src.table  # cached on the image object
+    desc = engine._remap_desc(cam.get_coordinate_map().rays, src, 3)
+    assert desc.src.lens == _native.LENS_TABLE and desc.src.lens_table_n == LENS_TABLE_SAMPLES
+    assert ctypes.addressof(desc.src.lens_table.contents) == src.table.ctypes.data
+    other = CameraImage(np.zeros((64, 80, 3), np.uint8), np.pi * 0.9, Lens(custom.forward_function, custom.reverse_function),
+                        magnitude=31.5)
+    desc2 = engine._remap_desc(other.get_coordinate_map().rays, other._source_geometry(), 3)
+    assert bytes(desc) != bytes(desc2) and engine._desc_key(desc) == engine._desc_key(desc2)
+    # C-ABI validation without a GPU: a table lens without a table is refused
+    lib = _native.load()
+    bad = _native.RemapDesc.from_buffer_copy(bytes(desc))
+    bad.src.lens_table = None
+    fake = ctypes.c_void_p(256)
+    assert lib.pb_remap_u8(ctypes.byref(bad), fake, 0, fake, 0, 1, None) == _native.PB_ERR_INVALID_ARGUMENT
+    assert b"PB_LENS_TABLE" in lib.pb_last_error()

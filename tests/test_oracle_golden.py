@@ -205,3 +205,16 @@ def test_c_port_config5_frames_at_full_size():
         image = workloads.source_image(wl, frame=k)
         assert _sha(image) == golden[k]["src_sha256"]
         assert _sha(c_port.remap(wl["out"], wl["rotations"], wl["src"], image)) == golden[k]["out_sha256"], k
+
+
+def test_numpy_port_map_projection_matches_the_reference(golden_small):
+    """oracle.numpy_port.map_projection vs the live reference's map_projection outputs
+    (tests/golden/map_projection.npz, made by make_golden_mapproj.py), incl. the in-place zeroing."""
+    _, _, maps = golden_small
+    golden = np.load(os.path.join(GOLDEN, "map_projection.npz"))
+    assert len(golden.files) >= 20
+    for key in golden.files:
+        cmap = maps[key].copy()
+        assert np.array_equal(numpy_port.map_projection(cmap), golden[key]), key
+        invalid = cmap[:, :, 2] != 0
+        assert np.all(cmap[invalid, :2] == 0)
