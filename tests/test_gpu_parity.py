@@ -727,6 +727,8 @@ def test_map_projection_on_device(torch_cuda, golden_small):
         assert got.dtype == np.uint8 and np.array_equal(got, golden[key]), key
         assert np.all(cmap[cmap[:, :, 2] != 0, :2] == 0), key
         oname, rname = key.split("__")
+        if "stereographic-360" in oname:
+            continue  # infinite image radius: the largest latitude (the stretch of the red channel) hangs on the last ulp of libm
         lazy = map_projection(helpers.product_map(geoms[oname], rotsets[rname]))
         diff = np.abs(lazy.astype(np.int16) - golden[key].astype(np.int16))
         diff = np.minimum(diff, 256 - diff)  # the green channel wraps (negative longitudes)
