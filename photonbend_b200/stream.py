@@ -135,6 +135,54 @@ def _device_worker(device: int, frames: Sequence[int], source, cmap, in_files, o
     return launches
 
 
+def remap_jpeg_stream(source, coordinate_map: CoordinateMap, jpegs: Sequence[bytes], devices: Optional[Sequence[int]] = None,
+                      batch: int = 4) -> List[bytes]:
+    """Compressed stream in memory: JPEG bytes in -> nvJPEG decode on the device -> ONE remap launch
+    per ``batch`` frames -> nvJPEG encode on the device -> JPEG bytes out.  Frame k on GPU
+    ``devices[k mod G]``, one host thread per GPU; raw pixels never cross PCIe."""
+    if not (isinstance(coordinate_map, CoordinateMap) and coordinate_map.is_lazy):
+        raise ValueError("remap_jpeg_stream needs the lazy CoordinateMap of get_coordinate_map()")
+    torch = engine._torch()
+    if devices is None:
+        devices = list(range(torch.cuda.device_count()))
+    devices = list(devices)[: max(1, len(jpegs))]
+    shape = tuple(source.image.shape)[-3:]  # (H, W, C) of one frame (the image may be a batch)
+    out: List[Optional[bytes]] = [None] * len(jpegs)
+    errors = []
+
+    def run(g):
+        try:
+            device = devices[g]
+            frames = list(shard_frames(len(jpegs), g, len(devices)))
+            with torch.cuda.device(device):
+                rays, geom = coordinate_map.rays, source._source_geometry()
+                src = torch.empty((batch,) + shape, dtype=torch.uint8, device=f"cuda:{device}")
+                dst = torch.empty((batch, rays.out.height, rays.out.output_width, shape[2]), dtype=torch.uint8,
+                                  device=f"cuda:{device}")
+                for c0 in range(0, len(frames), batch):
+                    chunk = frames[c0:c0 + batch]
+                    for i, k in enumerate(chunk):
+                        image_io.decode_jpeg_into(jpegs[k], src[i])
+                    n = len(chunk)
+                    if n == 1:
+                        engine.remap_device(rays, geom, src[0], dst[0])
+                    else:
+                        engine.remap_device(rays, geom, src[:n], dst[:n])
+                    for i, k in enumerate(chunk):
+                        out[k] = image_io.encode_jpeg_from_device(dst[i])
+        except BaseException as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=run, args=(g,)) for g in range(len(devices))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out  # type: ignore[return-value]
+
+
 def remap_files(source, coordinate_map: CoordinateMap, in_files: Sequence, out_files: Sequence,
                 devices: Optional[Sequence[int]] = None, depth: int = 3, batch: int = 1,
                 codec: Optional[str] = None, codec_threads: int = 4) -> dict:
@@ -151,7 +199,7 @@ def remap_files(source, coordinate_map: CoordinateMap, in_files: Sequence, out_f
     if devices is None:
         devices = list(range(torch.cuda.device_count()))
     devices = list(devices)[: max(1, len(in_files))]
-    shape = tuple(source.image.shape)
+    shape = tuple(source.image.shape)[-3:]  # (H, W, C) of one frame
     on_device = codec == "nvjpeg" and len(shape) == 3 and shape[2] == 3 and all(
         Path(p).suffix.lower() in (".jpg", ".jpeg") for p in list(in_files) + list(out_files))
     results, errors = [0] * len(devices), []

@@ -7,7 +7,7 @@
 # 4. summaries (.txt) and traffic_<tag>.json made here (ncu is on the box); copy them to profiles/
 tag=${1:-r2}
 out=gpurun_out
-small="--steps 5 --warmup 3 --no-cpu-baseline --no-also --e2e-steps 1 --sustain-seconds 0 --no-parity"
+small="--steps 5 --warmup 3 --no-cpu-baseline --no-also --e2e-steps 1 --sustain-seconds 0 --no-parity --no-compressed"
 python bench.py > $out/bench_${tag}.json 2> $out/bench_${tag}.err || exit 1
 python bench.py --impl reference --steps 5 --warmup 1 > $out/bench_ref_${tag}.json 2> $out/bench_ref_${tag}.err
 python bench.py $small > $out/plain_${tag}.log 2>&1 &&

@@ -12,6 +12,7 @@ import argparse
 import csv
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -74,7 +75,7 @@ def main():
         table[key] = {"bytes": int(read + write), "read": int(read), "write": int(write), "us_serialised": round(us, 2),
                       "inst_per_px": round(inst * 32 / px, 1), "fp64_pipe_pct": round(fp64 / us, 1),
                       "issue_active_pct": round(issue / us, 1), "kernels": kernels,
-                      "source": f"profiles/{os.path.basename(rep).replace('.ncu-rep', '.txt').replace('prof_', '')}"}
+                      "source": "profiles/" + re.sub(r"^prof_([^_]+)_", r"\1_ncu_full_", os.path.basename(rep)).replace(".ncu-rep", ".txt")}
     with open(args.out, "w") as fh:
         json.dump(table, fh, indent=1)
     print(json.dumps({k: (v if k == "_comment" else {kk: v[kk] for kk in ("bytes", "us_serialised", "inst_per_px")})
