@@ -463,6 +463,10 @@ __global__ void __launch_bounds__(256, PB_DIRECT_MIN_CTAS) remap_direct_kernel(c
 // the queue off with all lanes busy -- lane t takes entry t, whoever's pixel it is -- through the
 // float64 tiers.  Run in place, a pixel in a hundred would put 1 - 0.99^32 = 27 % of the warps
 // through the float64 code with one active lane.
+#ifndef PB_DIRECT32_UNROLL
+#define PB_DIRECT32_UNROLL 4
+#endif
+constexpr int kDirect32Unroll = PB_DIRECT32_UNROLL;
 template <int OUT_KIND, int SRC_KIND>
 __global__ void __launch_bounds__(256, PB_DIRECT_MIN_CTAS) remap_direct32_kernel(const __grid_constant__ RemapArgs a) {
     static_assert(SRC_KIND != PB_KIND_DOUBLE, "single-slot sources only");
@@ -472,20 +476,26 @@ __global__ void __launch_bounds__(256, PB_DIRECT_MIN_CTAS) remap_direct32_kernel
     const int row0 = a.row_begin + blockIdx.y * kTileH, col0 = blockIdx.x * kTileW;
     const int i0 = row0 + (tid >> 3), j0 = col0 + 4 * (tid & 7);
     int qn = 0;
+    // the four pixels of a quad share their row: unrolled, so that what depends on the row alone is
+    // computed once and four independent chains are in flight (PB_DIRECT32_UNROLL=1: one by one)
 #pragma unroll 1
-    for (int p = 0; p < kPxPerThread; ++p) {
-        const int i = i0 + (p >> 2) * 32, j = j0 + (p & 3);
-        bool need = false;
-        int xy = kNoPixel;
-        if (i < a.row_end && j < a.out.W) {
-            Lookup L;
-            if (a.fast.f32.enabled && fast32_lookup<OUT_KIND, SRC_KIND>(a.out, a.fast.f32, a.src, i, j, L)) xy = L.xy0;
-            else need = true;
+    for (int q = 0; q < kRowsPerThread; ++q) {
+        const int i = i0 + q * 32;
+#pragma unroll kDirect32Unroll
+        for (int k = 0; k < 4; ++k) {
+            const int p = q * 4 + k, j = j0 + k;
+            bool need = false;
+            int xy = kNoPixel;
+            if (i < a.row_end && j < a.out.W) {
+                Lookup L;
+                if (a.fast.f32.enabled && fast32_lookup<OUT_KIND, SRC_KIND>(a.out, a.fast.f32, a.src, i, j, L)) xy = L.xy0;
+                else need = true;
+            }
+            xybuf[w][p][lane] = xy;
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (need) queue[w][qn + __popc(m & ((1u << lane) - 1u))] = (unsigned char)(lane | (p << 5));
+            qn += __popc(m);
         }
-        xybuf[w][p][lane] = xy;
-        const unsigned m = __ballot_sync(0xffffffffu, need);
-        if (need) queue[w][qn + __popc(m & ((1u << lane) - 1u))] = (unsigned char)(lane | (p << 5));
-        qn += __popc(m);
     }
     __syncwarp();
 #pragma unroll 1

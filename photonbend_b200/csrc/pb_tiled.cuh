@@ -144,6 +144,17 @@ __global__ void __launch_bounds__(256) pb_tables_kernel(const __grid_constant__ 
 // second word of a gather only where the pixel runs into it: fewer active lanes, fewer bank
 // conflicts (8K target x16 0.725 -> 0.744 of the roofline, cfg5 x16 0.503 -> 0.509)
 #define PB_LEAN_PICK ptx::lds_pixel_sparse
+// ... except for the two-lens / blend-band class of a double-fisheye source, which is bound by its
+// own instruction stream at 16 warps per SM, not by the shared-memory pipe (cfg5 by parts,
+// profiles/experiments/README.md): there both words are always loaded (3 instructions per gather
+// instead of 6).  PB_CLS2_DENSE_PICK=0 to compare.
+#ifndef PB_CLS2_DENSE_PICK
+#define PB_CLS2_DENSE_PICK 1
+#endif
+template <bool DENSE>
+__device__ __forceinline__ unsigned lean_pick(unsigned word_sa, unsigned offset, unsigned shift) {
+    return DENSE ? ptx::lds_pixel(word_sa, offset, shift) : ptx::lds_pixel_sparse(word_sa, offset, shift);
+}
 
 constexpr int kMaxGroups = 8;  // frames in flight per tile (lean loop)
 
@@ -797,6 +808,7 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                 wmode[q] = fix_weights(wrow[q][0], wrow[q][1], wfix[q][0], wfix[q][1]) ? 1 : 2;
         }
         __syncthreads();  // the groups' zero bytes are in place
+        constexpr bool DENSE = (CLS == 2) && (PB_CLS2_DENSE_PICK != 0);
         auto frame_loop = [&](auto ACT, auto WGT) {
             constexpr int act = decltype(ACT)::value;  // 1: slot 0 only, 2: slot 1 only, 3: both
             constexpr bool wgt = decltype(WGT)::value;  // some row of the tile has a weighted blend
@@ -813,8 +825,8 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                     unsigned w[kPxPerThread];
 #pragma unroll
                     for (int p = 0; p < kPxPerThread; ++p) {
-                        v[p] = (act & 1) ? PB_LEAN_PICK(adr[0][p], goff, shf[0][p]) : 0u;
-                        w[p] = (act & 2) ? PB_LEAN_PICK(adr[S1][p], goff, shf[S1][p]) : 0u;
+                        v[p] = (act & 1) ? lean_pick<DENSE>(adr[0][p], goff, shf[0][p]) : 0u;
+                        w[p] = (act & 2) ? lean_pick<DENSE>(adr[S1][p], goff, shf[S1][p]) : 0u;
                     }
 #pragma unroll
                     for (int q = 0; q < kRowsPerThread; ++q) {
@@ -835,12 +847,12 @@ remap_tiled_kernel(const __grid_constant__ TiledArgs a) {
                 } else {
                     if (act & 1) {
 #pragma unroll
-                        for (int p = 0; p < kPxPerThread; ++p) v[p] = PB_LEAN_PICK(adr[0][p], goff, shf[0][p]);
+                        for (int p = 0; p < kPxPerThread; ++p) v[p] = lean_pick<DENSE>(adr[0][p], goff, shf[0][p]);
                     }
                     if (act & 2) {
 #pragma unroll
                         for (int p = 0; p < kPxPerThread; ++p) {
-                            const unsigned w = PB_LEAN_PICK(adr[S1][p], goff, shf[S1][p]);
+                            const unsigned w = lean_pick<DENSE>(adr[S1][p], goff, shf[S1][p]);
                             v[p] = (act & 1) ? __vadd4(v[p], w) : w;
                         }
                     }
