@@ -18,6 +18,7 @@
 #include "pb_tiled.cuh"
 #include "pb_sep1.cuh"
 #include "pb_chunk.cuh"
+#include "pb_tiled2.cuh"
 
 namespace pb {
 
@@ -901,6 +902,23 @@ static cudaError_t launch_chunk_one(const TiledArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// the two-lens / blend-band class of a batch with 512 threads per CTA (pb_tiled2.cuh)
+static cudaError_t launch_two_lens(const TiledArgs& a, cudaStream_t st) {
+    const int smem = two_lens_smem_bytes(a.stage_bytes);
+    static int max_smem_set[kMaxDevices] = {0};
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev)) return e;
+    if (dev < 0 || dev >= kMaxDevices || smem > max_smem_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(remap_two_lens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < kMaxDevices) max_smem_set[dev] = smem;
+    }
+    if (a.n_list <= 0) return cudaSuccess;
+    remap_two_lens_kernel<<<a.n_list, kTile2Threads, smem, st>>>(a);
+    PB_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
 // tuning experiments
 static int env_int(const char* name, int fallback) {
     const char* e = std::getenv(name);
@@ -1562,6 +1580,11 @@ static int plan_run(pb_plan& p, const double* tables, const uint8_t* src, int64_
                 } else if (chunk & 1) {
                     a.stage_bytes = env_int("PB_CHUNK_REST_KIB", 94) * 1024;
                     e = launch_chunk_one<PB_KIND_DOUBLE, 2>(a, lane ? lane->side : st);
+                } else if (env_int("PB_CLS2_THREADS", 512) == 512) {
+                    // 16 warps per CTA, one quad per thread: twice the warps per SM for the same shared memory
+                    // (cfg5 x16: the class alone 0.321 -> 0.301 ms, the step 0.628 -> 0.612 ms)
+                    a.stage_bytes = 2 * a.stage_bytes;  // (the ring of frame groups spans what were two stage buffers)
+                    e = launch_two_lens(a, lane ? lane->side : st);
                 } else {
                     e = launch_tiled_one<PB_KIND_EQUIRECT, PB_KIND_DOUBLE, 1, 2>(a, lane ? lane->side : st);
                 }

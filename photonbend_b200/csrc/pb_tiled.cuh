@@ -371,7 +371,7 @@ __device__ __noinline__ void direct_tile(const TiledArgs& a, const int* xy_scrat
             if (tid == 0) ptx::bulk_wait_read0();
             __syncthreads();
         }
-        for (int e = tid; e < kTileW * kTileH; e += kTileThreads) {
+        for (int e = tid; e < kTileW * kTileH; e += (int)blockDim.x) {
             const int r = e / kTileW, c = e - r * kTileW;
             const int i = min(y0 + r, a.out.H - 1), j = min(x0 + c, a.out.W - 1);
             Lookup L;

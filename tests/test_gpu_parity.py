@@ -342,7 +342,8 @@ def test_double_source_batches_blend_band(torch_cuda, fov_deg, monkeypatch):
     ])
     want = [numpy_port.remap(og, (), sg, f) for f in frames]
     dev = torch.from_numpy(frames).cuda()
-    for env in ({}, {"PB_ONE_BYTES": "4096", "PB_REST_KIB": "8"}, {"PB_CLASS_SPLIT": "0"}):
+    for env in ({}, {"PB_ONE_BYTES": "4096", "PB_REST_KIB": "8"}, {"PB_CLASS_SPLIT": "0"}, {"PB_CLS2_THREADS": "256"},
+                {"PB_CHUNK": "3"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         out = helpers.product_image(sg, dev).process_coordinate_map(helpers.product_map(og, ())).cpu().numpy()
