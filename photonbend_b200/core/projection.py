@@ -54,17 +54,20 @@ def _custom_lens_table(image, lens: int, role: str, height: int, width: int):
     [0, largest pixel radius in focal units] -- cached on the image object; (None, 0) for the
     built-in models."""
     if lens != _native.LENS_TABLE:
-        return None, 0.0
+        return None, 0.0, b""
     cache = image.__dict__.setdefault("_lens_tables", {})
     key = (role, height, width, float(image.f_distance))
     if key not in cache:
+        import hashlib
+
         if role == "source":
             x_max = float(np.pi)
             fn = image.forward_lens
         else:
             x_max = float(np.hypot((width - 1) / 2.0, (height - 1) / 2.0) / image.f_distance) * (1.0 + 1e-9) + 1e-12
             fn = image.reverse_lens
-        cache[key] = (lens_table(fn, x_max), x_max)
+        table = lens_table(fn, x_max)
+        cache[key] = (table, x_max, hashlib.sha1(table.tobytes()).digest())
     return cache[key]
 
 
@@ -164,10 +167,11 @@ class CameraImage(_DeviceSampler):
     def _geometry(self, role: str) -> engine.ImageGeometry:
         height, width = _frame_shape(self.image)
         lens = lens_id(self.forward_lens, self.reverse_lens)
-        table, table_max = _custom_lens_table(self, lens, role, height, width)
+        table, table_max, table_key = _custom_lens_table(self, lens, role, height, width)
         return engine.ImageGeometry(
             kind=_native.KIND_CAMERA, height=height, width=width, lens=lens,
-            fov=float(self.fov), f_distance=float(self.f_distance), table=table, table_max=table_max)
+            fov=float(self.fov), f_distance=float(self.f_distance), table=table, table_max=table_max,
+            table_key=table_key)
 
     def _source_geometry(self):
         return self._geometry("source")
@@ -202,10 +206,11 @@ class DoubleCameraImage(_DeviceSampler):
     def _geometry(self, role: str) -> engine.ImageGeometry:
         height, width = _frame_shape(self.image)
         lens = lens_id(self.forward_lens, self.reverse_lens)
-        table, table_max = _custom_lens_table(self, lens, role, height, width // 2)
+        table, table_max, table_key = _custom_lens_table(self, lens, role, height, width // 2)
         return engine.ImageGeometry(
             kind=_native.KIND_DOUBLE, height=height, width=width, lens=lens,
-            fov=float(self.sensor_fov), f_distance=float(self.f_distance), table=table, table_max=table_max)
+            fov=float(self.sensor_fov), f_distance=float(self.f_distance), table=table, table_max=table_max,
+            table_key=table_key)
 
     def _source_geometry(self):
         return self._geometry("source")

@@ -93,9 +93,12 @@ __global__ void __launch_bounds__(256) pb_sep1_slices_kernel(const double* __res
 // The 3 bytes of the staged pixel at byte offset off.  Single-lens source: the second word is
 // loaded only by the lanes that need it (T x1 47.0 -> 45.4 us); double source: both words always
 // (the predicate costs more than the conflicts it saves there: 74.4 vs 76.2 us).
+#ifndef PB_SEP1_PRED
+#define PB_SEP1_PRED 1
+#endif
 template <bool PRED>
 __device__ __forceinline__ unsigned sep1_pick(unsigned stage_sa, int off) {
-    if (PRED) return ptx::lds_pixel_pred(stage_sa + (unsigned)off);
+    if (PRED && PB_SEP1_PRED) return ptx::lds_pixel_pred(stage_sa + (unsigned)off);
     return ptx::lds_pixel(stage_sa, (unsigned)off & ~3u, (unsigned)off << 3);
 }
 
@@ -162,7 +165,13 @@ remap_sep1_kernel(const __grid_constant__ TiledArgs a) {
         const int u = blockIdx.x + k * G;
         ring[k * 2 + s] = (u < n_tiles) ? __ldg(tab + u * NSLOT + s) : make_int4(0, 0, 0, 0);
     }
+    // Programmatic dependent launch: the next grid on this stream may be set up while this one
+    // runs, and everything above -- barriers, zero bytes, descriptors out of the plan's tables,
+    // which no kernel writes after the plan was made -- ran before the grids ahead of this one had
+    // finished.  From here on the source image and the output buffer are touched: wait for them.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // one thread: the box loads of the tile whose descriptors sit in ring slot r, into stage buffer b
     auto issue = [&](int r, int b) {

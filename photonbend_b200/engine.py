@@ -33,6 +33,7 @@ class ImageGeometry:
     # remap evaluates, on [0, table_max] (see include/pb_remap.h: pb_image_desc.lens_table)
     table: Optional[np.ndarray] = field(default=None, compare=False)
     table_max: float = 0.0
+    table_key: bytes = b""  # digest of ``table``: what two geometries with user lenses are compared by
 
     @property
     def output_width(self) -> int:
@@ -52,6 +53,8 @@ class ImageGeometry:
     def table_digest(self) -> bytes:
         if self.table is None:
             return b""
+        if self.table_key:
+            return self.table_key
         import hashlib
 
         return hashlib.sha1(self.table.tobytes()).digest()
@@ -87,7 +90,22 @@ def _stream_ptr(torch) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_desc_memo: dict = {}  # (rays, src, channels) -> filled descriptor: a stream of calls through one geometry fills it once
+
+
 def _remap_desc(rays: RayPlan, src: ImageGeometry, channels: int) -> _native.RemapDesc:
+    memo_key = (rays, src, channels)
+    hit = _desc_memo.get(memo_key)
+    if hit is not None:
+        return hit
+    d = _build_remap_desc(rays, src, channels)
+    if len(_desc_memo) >= 64:
+        _desc_memo.pop(next(iter(_desc_memo)))
+    _desc_memo[memo_key] = d
+    return d
+
+
+def _build_remap_desc(rays: RayPlan, src: ImageGeometry, channels: int) -> _native.RemapDesc:
     if len(rays.rotations) > _native.PB_MAX_ROTATIONS:
         raise _native.NativeError(_native.PB_ERR_TOO_MANY_ROTATIONS, "too many rotations to fuse")
     d = _native.RemapDesc()
@@ -109,12 +127,18 @@ def _remap_desc(rays: RayPlan, src: ImageGeometry, channels: int) -> _native.Rem
 def _desc_key(desc: _native.RemapDesc) -> bytes:
     """Identity of a remap for the plan cache: the descriptor's bytes with the host pointers of
     lens tables replaced by a digest of what they point at."""
+    key = getattr(desc, "_key", None)
+    if key is not None:
+        return key
     tables = getattr(desc, "_tables", b"")
     if not tables:
-        return bytes(desc)
-    clone = _native.RemapDesc.from_buffer_copy(bytes(desc))
-    clone.out.lens_table = clone.src.lens_table = None
-    return bytes(clone) + tables
+        key = bytes(desc)
+    else:
+        clone = _native.RemapDesc.from_buffer_copy(bytes(desc))
+        clone.out.lens_table = clone.src.lens_table = None
+        key = bytes(clone) + tables
+    desc._key = key
+    return key
 
 
 class _PlanCache:

@@ -38,6 +38,13 @@ def main():
     for item in args.items:
         name, _, fr = item.partition(":")
         frames = int(fr or 1)
+        if frames == 1:
+            # one frame per launch: 20 launches as one CUDA graph over a pool of frames larger than L2
+            r = bench.quick_kernel_rate(torch, name, 1, steps=args.steps, warmup=args.warmup)
+            print(f"{args.tag:24s} {name:5s} x1   {r['ms_per_launch']:8.4f} ms  {r['value']:8.1f} Gpix/s  "
+                  f"frac {r['roofline']['frac']:.3f}  (events around each launch: {r['ms_per_launch_events_around_each']:.4f} ms)",
+                  flush=True)
+            continue
         wl = workloads.WORKLOADS[name]
         batch = bench.make_device_batch(torch, name, frames, 0)
         source = helpers.product_image(wl["src"], batch)

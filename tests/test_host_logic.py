@@ -166,7 +166,13 @@ def test_user_defined_lens_becomes_a_table():
     other = CameraImage(np.zeros((64, 80, 3), np.uint8), np.pi * 0.9, Lens(custom.forward_function, custom.reverse_function),
                         magnitude=31.5)
     desc2 = engine._remap_desc(other.get_coordinate_map().rays, other._source_geometry(), 3)
-    assert bytes(desc) != bytes(desc2) and engine._desc_key(desc) == engine._desc_key(desc2)
+    # same geometry, same table CONTENT (another array at another address): one descriptor, one plan
+    assert other._source_geometry().table is not src.table
+    assert engine._desc_key(desc) == engine._desc_key(desc2)
+    third = CameraImage(np.zeros((64, 80, 3), np.uint8), np.pi * 0.9,
+                        Lens(lambda t: 2.0001 * np.sin(t / 2), custom.reverse_function), magnitude=31.5 * 2.0001 / 2)
+    desc3 = engine._remap_desc(third.get_coordinate_map().rays, third._source_geometry(), 3)
+    assert engine._desc_key(desc3) != engine._desc_key(desc)  # another forward function: another plan
     # C-ABI validation without a GPU: a table lens without a table is refused
     lib = _native.load()
     bad = _native.RemapDesc.from_buffer_copy(bytes(desc))
