@@ -120,46 +120,36 @@ __device__ __forceinline__ int out_vector32(const OutGeom& g, const Fast32GeomT<
     if (!(r2 < fg.r2_domain)) return 2;
     if (!(r2 < fg.r2_valid)) return (r2 > fg.r2_invalid) ? 1 : 2;
     const T inv_f = fg.inv_f;
+    const int lens = g.lens;  // (uniform: an if-chain costs two instructions per test, a jump table seven)
     T k;  // sin(lat) / r
-    switch (g.lens) {
-        case PB_LENS_EQUISOLID: {
-            const T u2 = r2 * fg.quarter_inv_f2;
-            const T w = (T)1 - u2;
-            k = w * O::rsqrt(w) * inv_f;
-            vy = O::fma((T)-2, u2, (T)1);
-            break;
-        }
-        case PB_LENS_ORTHOGRAPHIC: {
-            k = inv_f;
-            const T w = O::fma(-r2, inv_f * inv_f, (T)1);
-            vy = w * O::rsqrt(w);
-            break;
-        }
-        case PB_LENS_STEREOGRAPHIC: {
-            const T t2 = r2 * fg.quarter_inv_f2;
-            const T w = O::rcp((T)1 + t2);
-            k = inv_f * w;
-            vy = ((T)1 - t2) * w;
-            break;
-        }
-        case PB_LENS_RECTILINEAR: {
-            const T s = O::rsqrt(O::fma(r2, inv_f * inv_f, (T)1));
-            k = inv_f * s;
-            vy = s;
-            break;
-        }
-        default: {
-            if (!(r2 > (T)0.25)) return 2;  // the centre pixel: longitude undefined
-            const T inv_r = O::rsqrt(r2);
-            const T d = r2 * inv_r * inv_f;
-            T lat = d;
-            if (g.lens != PB_LENS_EQUIDISTANT) lat = O::asin(d * (T)(1.0 / 1.47)) * (T)(1.0 / 0.713);
-            T sl, cl;
-            O::sincos(lat, &sl, &cl);
-            k = sl * inv_r;
-            vy = cl;
-            break;
-        }
+    if (lens == PB_LENS_EQUISOLID) {
+        const T u2 = r2 * fg.quarter_inv_f2;
+        const T w = (T)1 - u2;
+        k = w * O::rsqrt(w) * inv_f;
+        vy = O::fma((T)-2, u2, (T)1);
+    } else if (lens == PB_LENS_RECTILINEAR) {
+        const T s = O::rsqrt(O::fma(r2, inv_f * inv_f, (T)1));
+        k = inv_f * s;
+        vy = s;
+    } else if (lens == PB_LENS_STEREOGRAPHIC) {
+        const T t2 = r2 * fg.quarter_inv_f2;
+        const T w = O::rcp((T)1 + t2);
+        k = inv_f * w;
+        vy = ((T)1 - t2) * w;
+    } else if (lens == PB_LENS_ORTHOGRAPHIC) {
+        k = inv_f;
+        const T w = O::fma(-r2, inv_f * inv_f, (T)1);
+        vy = w * O::rsqrt(w);
+    } else {
+        if (!(r2 > (T)0.25)) return 2;  // the centre pixel: longitude undefined
+        const T inv_r = O::rsqrt(r2);
+        const T d = r2 * inv_r * inv_f;
+        T lat = d;
+        if (lens != PB_LENS_EQUIDISTANT) lat = O::asin(d * (T)(1.0 / 1.47)) * (T)(1.0 / 0.713);
+        T sl, cl;
+        O::sincos(lat, &sl, &cl);
+        k = sl * inv_r;
+        vy = cl;
     }
     vx = x * k;
     vz = y * k;
@@ -172,47 +162,45 @@ template <typename T>
 __device__ __forceinline__ int lens_q32(int lens, const Fast32GeomT<T>& fg, T ny, T h, T inv_h, T& q, T& amp) {
     using O = F32Ops<T>;
     const T f = fg.src_f;
-    switch (lens) {
-        case PB_LENS_EQUIDISTANT: {
-            const T theta = atan2_32(h, ny);
-            q = theta * f * inv_h;
-            amp = O::fma((T)1.4, f, q);
-            return 0;
-        }
-        case PB_LENS_EQUISOLID: {
-            const T w = (T)1 + ny;
-            if (!(w > (T)1e-3)) return 2;
-            q = f * O::rsqrt((T)0.5 * w);
-            amp = (T)0.5 * q * h * O::rcp(w);
-            return 0;
-        }
-        case PB_LENS_ORTHOGRAPHIC:
-            q = f;
-            amp = (T)0;
-            return 0;
-        case PB_LENS_STEREOGRAPHIC: {
-            const T w = (T)1 + ny;
-            if (!(w > (T)1e-3)) return 2;
-            const T iw = O::rcp(w);
-            q = (T)2 * f * iw;
-            amp = q * h * iw;
-            return 0;
-        }
-        case PB_LENS_RECTILINEAR:
-            if (ny > fg.ny_rect_in) {
-                const T iy = O::rcp(ny);
-                q = f * iy;
-                amp = q * h * iy;
-                return 0;
-            }
-            return (ny < fg.ny_rect_out) ? 1 : 2;
-        default: {
-            const T theta = atan2_32(h, ny);
-            q = (T)1.47 * O::sin((T)0.713 * theta) * f * inv_h;
-            amp = O::fma((T)1.5, f, q);
-            return 0;
-        }
+    if (lens == PB_LENS_EQUIDISTANT) {
+        const T theta = atan2_32(h, ny);
+        q = theta * f * inv_h;
+        amp = O::fma((T)1.4, f, q);
+        return 0;
     }
+    if (lens == PB_LENS_EQUISOLID) {
+        const T w = (T)1 + ny;
+        if (!(w > (T)1e-3)) return 2;
+        q = f * O::rsqrt((T)0.5 * w);
+        amp = (T)0.5 * q * h * O::rcp(w);
+        return 0;
+    }
+    if (lens == PB_LENS_STEREOGRAPHIC) {
+        const T w = (T)1 + ny;
+        if (!(w > (T)1e-3)) return 2;
+        const T iw = O::rcp(w);
+        q = (T)2 * f * iw;
+        amp = q * h * iw;
+        return 0;
+    }
+    if (lens == PB_LENS_RECTILINEAR) {
+        if (ny > fg.ny_rect_in) {
+            const T iy = O::rcp(ny);
+            q = f * iy;
+            amp = q * h * iy;
+            return 0;
+        }
+        return (ny < fg.ny_rect_out) ? 1 : 2;
+    }
+    if (lens == PB_LENS_ORTHOGRAPHIC) {
+        q = f;
+        amp = (T)0;
+        return 0;
+    }
+    const T theta = atan2_32(h, ny);
+    q = (T)1.47 * O::sin((T)0.713 * theta) * f * inv_h;
+    amp = O::fma((T)1.5, f, q);
+    return 0;
 }
 
 template <typename T, int OUT_KIND, int SRC_KIND>
@@ -291,20 +279,21 @@ __device__ __forceinline__ Coords32<T> coords32(const OutGeom& out, const Fast32
 // Index along an axis of n pixels for the centred coordinate v, centre = c_int + c_half * 0.5:
 // coordinate = c_int + (v + 0.5 c_half); the reference truncates toward zero and then tests
 // 0 <= index < n (projection.py:223-231, 254-259), so a coordinate in (-1, 0) is index 0.
-// decided: further than e from every integer (|v| < 2^21).
+// decided: further than e from every integer.  One conversion each way (F2I.FLOOR, I2F): a value
+// too large for an int saturates and a NaN converts to 0 -- either way the "fraction" fails the
+// test below and the pixel goes to the float64 tiers.
 struct Index32 {
     int idx;
     bool decided, inside;
 };
 __device__ __forceinline__ Index32 index32(float v, float e, int c_int, int c_half, int n) {
-    const float t = c_half ? v + 0.5f : v;
-    const float w = t + 12582912.0f;  // 1.5 * 2^23: the sum's mantissa holds round-to-nearest(t)
-    const int rn = (__float_as_int(w) & 0x7fffff) - 0x400000;
-    const float d = t - (w - 12582912.0f);
+    const float t = v + 0.5f * (float)c_half;
+    const int fr = __float2int_rd(t);          // floor of the centred coordinate
+    const float d = t - (float)fr;             // its fraction, exact
     Index32 r;
-    int fl = c_int + rn - (d < 0.0f ? 1 : 0);  // floor of the coordinate
-    r.decided = (fabsf(d) > e) && (fabsf(t) < 2097152.0f);
-    if (fl == -1) fl = 0;  // (-1, 0) truncates to 0
+    r.decided = fminf(d, 1.0f - d) > e;
+    int fl = c_int + fr;                       // floor of the coordinate
+    if (fl == -1) fl = 0;                      // (-1, 0) truncates to 0
     r.idx = fl;
     r.inside = (unsigned)fl < (unsigned)n;
     return r;

@@ -989,6 +989,8 @@ struct pb_plan {
     int max_units;       // widest staged row of any tile, in 16-byte units (one tensor map per width)
     int raster_band;     // tile rows per raster band (see remap_tiled_kernel)
     int sep1_cap;        // single-frame separable kernel: bytes per stage buffer
+    int sep1_cap3;       // ... single-lens source: buffer size at which THREE stage buffers keep four CTAs per SM
+                         //     and still hold (all but 3 % of) the tiles; 0 = two buffers
     double* luts;        // device: lens tables of PB_LENS_TABLE lenses (out.lut / src.lut point into it); null otherwise
     double* tables;      // device: col_tab [W][2], row_tab [H][4], then the per-tile footprints; null unless separable
     // separable double-fisheye source: the tiles sorted into two classes, each in raster order --
@@ -1066,6 +1068,7 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     p.max_units = 19;           // rows of up to 304 bytes = 101 source pixels
     p.raster_band = 16;
     p.sep1_cap = (d.src.kind == PB_KIND_DOUBLE ? 48 : 24) * 1024;  // un-tuned default
+    p.sep1_cap3 = 0;
     if (const char* e = std::getenv("PB_RASTER_BAND")) p.raster_band = std::atoi(e);  // tuning experiments
     p.luts = nullptr;
     p.tables = nullptr;
@@ -1366,6 +1369,26 @@ static void tune_stage(pb_plan& p, cudaStream_t st) {
                 if (kib > 96) kib = 96;
                 if (const char* e = std::getenv("PB_SEP1_KIB")) kib = std::atoi(e);  // tuning experiments
                 p.sep1_cap = kib * 1024;
+                // A third stage buffer (loads issued two tiles ahead instead of one) pays only while four
+                // CTAs still fit an SM: T x1 38.2 -> 37.2 us, cfg1 x1 24.9 -> 24.4 us at 13 KiB buffers,
+                // slower at 14 KiB (three CTAs) and at 12 KiB (more tiles gather from global memory).
+                if (p.src.kind == PB_KIND_CAMERA && counted > 0) {
+                    int dev = 0, smem_sm = 0, reserved = 1024;
+                    if (cudaGetDevice(&dev) == cudaSuccess &&
+                        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess) {
+                        (void)cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+                        const int budget = smem_sm / PB_SEP1_CAM_CTAS - reserved;
+                        int k3 = 0;
+                        while (sep1_smem_bytes((k3 + 1) * 1024, false, 3) <= budget) ++k3;
+                        int left_out = 0;
+                        for (int k = k3 + 1; k <= 128; ++k) left_out += hist[k];
+                        if (k3 >= 4 && left_out * 100 <= counted * 3) p.sep1_cap3 = k3 * 1024;
+                    }
+                    if (const char* e = std::getenv("PB_SEP1_BUFFERS")) {  // tuning experiments
+                        if (std::atoi(e) == 2) p.sep1_cap3 = 0;
+                        if (std::atoi(e) == 3) p.sep1_cap3 = std::min(p.sep1_cap, 13 * 1024);
+                    }
+                }
                 delete[] hist;
             }
         } else {
@@ -1427,9 +1450,13 @@ static cudaError_t fill_tables(const pb_plan& p, double* tables, cudaStream_t st
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int n_tiles = tiles_x(p) * tiles_y(p);
+    // launch order of the single-frame kernel: bands of 4 tile rows walked column by column (the
+    // resident CTAs then cover a more compact patch of the source than with the 16-row bands of the
+    // batched kernel: T x1 37.2 -> 36.8 us)
+    static const int sep1_band = env_int("PB_SEP1_RASTER_BAND", 4);
     pb_sep1_table_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(footprint_table(p, tables),
                                                               const_cast<int4*>(sep1_table(p, tables)), tiles_x(p),
-                                                              tiles_y(p), p.raster_band,
+                                                              tiles_y(p), p.src.kind == PB_KIND_CAMERA ? sep1_band : p.raster_band,
                                                               p.src.kind == PB_KIND_DOUBLE ? 2 : 1);
     PB_COUNT_LAUNCH();
     e = cudaGetLastError();
@@ -1544,13 +1571,16 @@ static int plan_run(pb_plan& p, const double* tables, const uint8_t* src, int64_
             cudaError_t e;
             if (sep && whole && n_frames == 1 && !sep1_off && p.out.W / kTileW < 65536 && p.out.H / kTileH < 32768)
             {
-                // two stage buffers; a third one (deeper prefetch) measured no faster on a single-lens
-                // source (T x1 41.5 us either way) and does not always fit: PB_SEP1_BUFFERS=3 for experiments
-                static const int nb_env = std::getenv("PB_SEP1_BUFFERS") ? std::atoi(std::getenv("PB_SEP1_BUFFERS")) : 0;
-                if (a.src.kind == PB_KIND_CAMERA)
-                    e = (nb_env == 3 && sep1_smem_bytes(a.sep1_cap, false, 3) <= kMaxTiledSmem)
-                            ? launch_sep1_one<PB_KIND_CAMERA, 3>(a, st)
-                            : launch_sep1_one<PB_KIND_CAMERA, 2>(a, st);
+                // single-lens source: three stage buffers where the plan found a buffer size that keeps
+                // four CTAs per SM (tune_stage), two otherwise
+                if (a.src.kind == PB_KIND_CAMERA) {
+                    if (p.sep1_cap3 > 0 && tables == p.tables) {
+                        a.sep1_cap = p.sep1_cap3;
+                        e = launch_sep1_one<PB_KIND_CAMERA, 3>(a, st);
+                    } else {
+                        e = launch_sep1_one<PB_KIND_CAMERA, 2>(a, st);
+                    }
+                }
                 else if (p.sep1_cls && tables == p.tables && !class_split_off()) {
                     // two grids by tile class, as for batches: the tiles that see both lenses (or the
                     // blend band) keep the two-rectangle buffers, those that see one lens run as a
