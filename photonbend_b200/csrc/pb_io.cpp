@@ -46,7 +46,8 @@ int codec_fail(nvjpegStatus_t s, const char* what) {
 // device current), each serialised by its own mutex: a caller decodes / encodes one image at a
 // time per GPU; the host threads that drive different GPUs do not wait for each other
 struct Codec {
-    std::mutex lock;
+    std::mutex lock;      // start-up and the decoder state
+    std::mutex enc_lock;  // the encoder state: a host thread may encode while another one decodes
     nvjpegHandle_t handle = nullptr;
     nvjpegJpegState_t dec_state = nullptr;
     nvjpegEncoderState_t enc_state = nullptr;
@@ -142,8 +143,12 @@ int pb_io_jpeg_encode_rgb_u8(const uint8_t* src, int32_t width, int32_t height, 
     }
     cudaStream_t st = (cudaStream_t)stream;
     Codec& c = codec();
-    std::lock_guard<std::mutex> guard(c.lock);
-    nvjpegStatus_t s = c.ensure();
+    nvjpegStatus_t s;
+    {
+        std::lock_guard<std::mutex> guard(c.lock);
+        s = c.ensure();
+    }
+    std::lock_guard<std::mutex> enc_guard(c.enc_lock);
     if (s == NVJPEG_STATUS_SUCCESS) s = c.ensure_encoder(st);
     if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_encode_rgb_u8 (nvjpeg start-up)");
     s = nvjpegEncoderParamsSetQuality(c.enc_params, quality, st);

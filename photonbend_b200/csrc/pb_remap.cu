@@ -553,8 +553,8 @@ __global__ void __launch_bounds__(256) fast32_stats_kernel(const __grid_constant
     atomicAdd(counters + 0, 1ULL);
     if (cf.status != 2 && cd.status != 2 && (cf.status != cd.status || cf.slot1 != cd.slot1)) atomicAdd(counters + 3, 1ULL);
     Lookup L;
-    if (!fast32_lookup<OUT_KIND, SRC_KIND>(a.out, a.fast.f32, a.src, i, j, L)) {
-        atomicAdd(counters + 1, 1ULL);
+    if (!a.fast.f32.enabled || !fast32_lookup<OUT_KIND, SRC_KIND>(a.out, a.fast.f32, a.src, i, j, L)) {
+        atomicAdd(counters + 1, 1ULL);  // (a tier that is switched off decides nothing)
     } else {
         const Lookup R = resolve_lookup64<OUT_KIND, SRC_KIND>(a.out, a.fast, a.rot, a.src, i, j);
         if (L.xy0 != R.xy0 || L.xy1 != R.xy1 || !(R.w0 == 1.0 && R.w1 == 1.0)) atomicAdd(counters + 2, 1ULL);

@@ -139,7 +139,8 @@ def remap_jpeg_stream(source, coordinate_map: CoordinateMap, jpegs: Sequence[byt
                       batch: int = 4) -> List[bytes]:
     """Compressed stream in memory: JPEG bytes in -> nvJPEG decode on the device -> ONE remap launch
     per ``batch`` frames -> nvJPEG encode on the device -> JPEG bytes out.  Frame k on GPU
-    ``devices[k mod G]``, one host thread per GPU; raw pixels never cross PCIe."""
+    ``devices[k mod G]``, two host threads per GPU (decode of the next batch overlaps remap + encode
+    of the current one); raw pixels never cross PCIe."""
     if not (isinstance(coordinate_map, CoordinateMap) and coordinate_map.is_lazy):
         raise ValueError("remap_jpeg_stream needs the lazy CoordinateMap of get_coordinate_map()")
     torch = engine._torch()
@@ -151,25 +152,64 @@ def remap_jpeg_stream(source, coordinate_map: CoordinateMap, jpegs: Sequence[byt
     errors = []
 
     def run(g):
+        # two host threads per GPU: this one decodes batch k + 1 into the other of two device
+        # buffers (nvJPEG's Huffman stage is host work) while the second one remaps and encodes batch k
         try:
             device = devices[g]
             frames = list(shard_frames(len(jpegs), g, len(devices)))
+            chunks = [frames[c0:c0 + batch] for c0 in range(0, len(frames), batch)]
             with torch.cuda.device(device):
                 rays, geom = coordinate_map.rays, source._source_geometry()
-                src = torch.empty((batch,) + shape, dtype=torch.uint8, device=f"cuda:{device}")
+                srcs = [torch.empty((batch,) + shape, dtype=torch.uint8, device=f"cuda:{device}") for _ in range(2)]
                 dst = torch.empty((batch, rays.out.height, rays.out.output_width, shape[2]), dtype=torch.uint8,
                                   device=f"cuda:{device}")
-                for c0 in range(0, len(frames), batch):
-                    chunk = frames[c0:c0 + batch]
-                    for i, k in enumerate(chunk):
-                        image_io.decode_jpeg_into(jpegs[k], src[i])
-                    n = len(chunk)
-                    if n == 1:
-                        engine.remap_device(rays, geom, src[0], dst[0])
-                    else:
-                        engine.remap_device(rays, geom, src[:n], dst[:n])
-                    for i, k in enumerate(chunk):
-                        out[k] = image_io.encode_jpeg_from_device(dst[i])
+                decoded = [threading.Semaphore(0), threading.Semaphore(0)]  # buffer b holds a decoded batch
+                free = [threading.Semaphore(1), threading.Semaphore(1)]     # buffer b may be overwritten
+                failed = []
+
+                streams = [torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)]
+
+                def consume():
+                    try:
+                        with torch.cuda.device(device), torch.cuda.stream(streams[1]):
+                            for n, chunk in enumerate(chunks):
+                                b = n & 1
+                                decoded[b].acquire()
+                                if failed:
+                                    return
+                                k = len(chunk)
+                                if k == 1:
+                                    engine.remap_device(rays, geom, srcs[b][0], dst[0])
+                                else:
+                                    engine.remap_device(rays, geom, srcs[b][:k], dst[:k])
+                                torch.cuda.current_stream().synchronize()
+                                free[b].release()  # the remap has read the batch: it may be decoded over
+                                for i, f in enumerate(chunk):
+                                    out[f] = image_io.encode_jpeg_from_device(dst[i])
+                    except BaseException as exc:  # noqa: BLE001
+                        failed.append(exc)
+                        for sem in free:
+                            sem.release()
+
+                consumer = threading.Thread(target=consume)
+                consumer.start()
+                try:
+                    with torch.cuda.stream(streams[0]):
+                        for n, chunk in enumerate(chunks):
+                            b = n & 1
+                            free[b].acquire()
+                            if failed:
+                                break
+                            for i, f in enumerate(chunk):
+                                image_io.decode_jpeg_into(jpegs[f], srcs[b][i])  # (synchronises its stream)
+                            decoded[b].release()
+                except BaseException as exc:  # noqa: BLE001
+                    failed.append(exc)
+                    for sem in decoded:
+                        sem.release()
+                consumer.join()
+                if failed:
+                    raise failed[0]
         except BaseException as exc:  # noqa: BLE001
             errors.append(exc)
 

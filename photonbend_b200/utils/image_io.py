@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from pathlib import Path
 
 import numpy as np
@@ -51,6 +52,7 @@ class CodecError(RuntimeError):
 
 
 _lib = None
+_encode_buffers = threading.local()
 
 
 def load_codec():
@@ -141,14 +143,25 @@ def encode_jpeg_from_device(pixels, quality: int = PILLOW_DEFAULT_QUALITY, subsa
     pixels = pixels.contiguous()
     lib = load_codec()
     h, w = int(pixels.shape[0]), int(pixels.shape[1])
-    capacity = h * w * 3 + 65536  # a baseline JPEG never outgrows its pixels by more than its tables
-    out = (ctypes.c_ubyte * capacity)()
-    size = ctypes.c_size_t(capacity)
-    with torch.cuda.device(pixels.device):
-        stream = torch.cuda.current_stream()
-        _check(lib, lib.pb_io_jpeg_encode_rgb_u8(ctypes.c_void_p(pixels.data_ptr()), w, h, int(quality), int(subsampling),
-                                                 ctypes.c_void_p(stream.cuda_stream), out, ctypes.byref(size)))
-    return bytes(memoryview(out)[: size.value])
+    # one bitstream buffer per host thread, grown on demand (the library reports the size it needs):
+    # a fresh h*w*3-byte buffer per frame is 88 MB of page faults for an 8K image
+    capacity = max(getattr(_encode_buffers, "capacity", 0), h * w // 4 + 65536)
+    for _ in range(2):
+        if getattr(_encode_buffers, "capacity", 0) < capacity:
+            _encode_buffers.buffer = (ctypes.c_ubyte * capacity)()
+            _encode_buffers.capacity = capacity
+        out = _encode_buffers.buffer
+        size = ctypes.c_size_t(_encode_buffers.capacity)
+        with torch.cuda.device(pixels.device):
+            stream = torch.cuda.current_stream()
+            code = lib.pb_io_jpeg_encode_rgb_u8(ctypes.c_void_p(pixels.data_ptr()), w, h, int(quality), int(subsampling),
+                                                ctypes.c_void_p(stream.cuda_stream), out, ctypes.byref(size))
+        if code == PB_IO_ERR_INVALID_ARGUMENT and size.value > _encode_buffers.capacity:
+            capacity = int(size.value) + 65536  # too small: the library said how much it needs
+            continue
+        _check(lib, code)
+        return bytes(memoryview(out)[: size.value])
+    raise CodecError(PB_IO_ERR_CODEC, "encode_jpeg_from_device: bitstream larger than the size the codec announced")
 
 
 # ------------------------------------------------------------------------------- files

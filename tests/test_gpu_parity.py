@@ -796,3 +796,47 @@ def test_user_defined_lens_through_tables(torch_cuda):
                 n_bad += int(diff.sum())
     print(f"user-defined lens tables: {n_bad} of {n_px} pixels differ from the built-in model")
     assert n_bad <= max(4, 2e-5 * n_px), (n_bad, n_px)
+
+
+def test_non_orthonormal_matrices_take_the_exact_chain(torch_cuda, monkeypatch):
+    """The raw ABI takes any 9 doubles as a rotation.  The short cuts carry the ray as a unit vector
+    through ONE composed matrix, which equals the reference's per-rotation acos / atan2 round trip
+    only for orthonormal matrices: anything else must switch them off (derive_fast) and give what
+    the exact chain gives."""
+    import ctypes
+
+    torch = torch_cuda
+    from oracle import numpy_port
+    from photonbend_b200 import _native, engine
+
+    lib = _native.load()
+    sg = {"kind": "camera", "height": 256, "width": 256, "lens": "equidistant", "fov": case_matrix.rad(360), "magnitude": 127.5}
+    image = case_matrix.case_image(sg, 21)
+    src = torch.from_numpy(image).cuda()
+    d = _native.RemapDesc()
+    d.out.kind, d.out.height, d.out.width = _native.KIND_EQUIRECT, 192, 384
+    d.src.kind, d.src.lens, d.src.height, d.src.width = _native.KIND_CAMERA, _native.LENS_EQUIDISTANT, 256, 256
+    d.src.fov, d.src.f_distance = sg["fov"], numpy_port.focal_distance(sg)
+    d.channels, d.n_rotations = 3, 2
+    rot = numpy_port.rotation_matrix(0.4, 0.5, 0.6)
+    shear = rot @ np.array([[1.0, 0.2, 0.0], [0.0, 0.9, 0.0], [0.0, 0.0, 1.0]])  # scaled and sheared
+    for k, m in enumerate((shear, rot)):
+        for e in range(9):
+            d.rotations[k][e] = m.reshape(9)[e]
+
+    def run():
+        dst = torch.zeros((192, 384, 3), dtype=torch.uint8, device="cuda")
+        rc = lib.pb_remap_u8(ctypes.byref(d), src.data_ptr(), 0, dst.data_ptr(), 0, 1, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.pb_last_error()
+        torch.cuda.synchronize()
+        return dst.cpu().numpy()
+
+    got = run()
+    monkeypatch.setenv("PB_EXACT_CHAIN", "1")
+    exact = run()
+    monkeypatch.delenv("PB_EXACT_CHAIN")
+    assert np.array_equal(got, exact)
+    stats = (ctypes.c_double * 6)()
+    assert lib.pb_debug_fast32_stats(ctypes.byref(d), stats, None) == 0
+    assert stats[3] == stats[2], "tier 1 must leave every pixel of a non-orthonormal remap undecided"
+    engine.clear_plan_cache()
