@@ -458,12 +458,11 @@ __global__ void __launch_bounds__(256, PB_DIRECT_MIN_CTAS) remap_direct_kernel(c
     }
 }
 
-// The same for a camera / panorama source with the undecided pixels of a warp COMPACTED: every
+// The same for a camera / panorama source with the undecided pixels of a warp DEFERRED: every
 // thread first runs tier 1 (float, pb_fast32.cuh) on its 8 pixels and parks the results in shared
-// memory; the ~1 % of pixels tier 1 could not decide are queued per warp, and the warp then works
-// the queue off with all lanes busy -- lane t takes entry t, whoever's pixel it is -- through the
-// float64 tiers.  Run in place, a pixel in a hundred would put 1 - 0.99^32 = 27 % of the warps
-// through the float64 code with one active lane.
+// memory; the ~2 % of pixels tier 1 could not decide are then resolved through the float64 tiers.
+// Run in place, two pixels in a hundred would put 1 - 0.98^32 = 48 % of the warps through the
+// float64 code at every one of the 8 pixel steps, with one active lane each time.
 #ifndef PB_DIRECT32_UNROLL
 #define PB_DIRECT32_UNROLL 4
 #endif
@@ -471,12 +470,11 @@ constexpr int kDirect32Unroll = PB_DIRECT32_UNROLL;
 template <int OUT_KIND, int SRC_KIND>
 __global__ void __launch_bounds__(256, PB_DIRECT_MIN_CTAS) remap_direct32_kernel(const __grid_constant__ RemapArgs a) {
     static_assert(SRC_KIND != PB_KIND_DOUBLE, "single-slot sources only");
-    __shared__ unsigned char queue[8][256];  // per warp: owner lane | pixel << 5
     __shared__ int xybuf[8][kPxPerThread][32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int row0 = a.row_begin + blockIdx.y * kTileH, col0 = blockIdx.x * kTileW;
     const int i0 = row0 + (tid >> 3), j0 = col0 + 4 * (tid & 7);
-    int qn = 0;
+    unsigned pend = 0;  // bit p: tier 1 left pixel p of this thread undecided
     // the four pixels of a quad share their row: unrolled, so that what depends on the row alone is
     // computed once and four independent chains are in flight (PB_DIRECT32_UNROLL=1: one by one)
 #pragma unroll 1
@@ -485,31 +483,28 @@ __global__ void __launch_bounds__(256, PB_DIRECT_MIN_CTAS) remap_direct32_kernel
 #pragma unroll kDirect32Unroll
         for (int k = 0; k < 4; ++k) {
             const int p = q * 4 + k, j = j0 + k;
-            bool need = false;
             int xy = kNoPixel;
             if (i < a.row_end && j < a.out.W) {
                 Lookup L;
                 if (a.fast.f32.enabled && fast32_lookup<OUT_KIND, SRC_KIND>(a.out, a.fast.f32, a.src, i, j, L)) xy = L.xy0;
-                else need = true;
+                else pend |= 1u << p;
             }
             xybuf[w][p][lane] = xy;
-            const unsigned m = __ballot_sync(0xffffffffu, need);
-            if (need) queue[w][qn + __popc(m & ((1u << lane) - 1u))] = (unsigned char)(lane | (p << 5));
-            qn += __popc(m);
         }
     }
-    __syncwarp();
-#pragma unroll 1
-    for (int b = 0; b < qn; b += 32) {
-        const int e = b + lane;
-        if (e < qn) {
-            const int code = queue[w][e];
-            const int ot = w * 32 + (code & 31), p = code >> 5;
-            const int i = row0 + (ot >> 3) + (p >> 2) * 32, j = col0 + 4 * (ot & 7) + (p & 3);
-            xybuf[w][p][code & 31] = resolve_lookup64<OUT_KIND, SRC_KIND>(a.out, a.fast, a.rot, a.src, i, j).xy0;
+    // The undecided pixels -- a percent or two, spread evenly -- are taken AFTER the float passes,
+    // every lane its own, one per round: a warp of 256 pixels has ~5 of them on ~5 different lanes,
+    // so it goes through the float64 tiers once or twice instead of at almost every one of the 8
+    // pixel steps (in place) -- and without the per-pixel ballot / queue bookkeeping a compacted
+    // queue costs (measured: that bookkeeping is dearer than the second round it saves).
+    while (__any_sync(0xffffffffu, pend != 0)) {
+        if (pend) {
+            const int p = __ffs(pend) - 1;
+            pend &= pend - 1;
+            const int i = i0 + (p >> 2) * 32, j = j0 + (p & 3);
+            xybuf[w][p][lane] = resolve_lookup64<OUT_KIND, SRC_KIND>(a.out, a.fast, a.rot, a.src, i, j).xy0;
         }
     }
-    __syncwarp();
     if (j0 >= a.out.W) return;
     const unsigned char* __restrict__ sp = a.src_px;
     const int src_pitch = a.src.W * 3;
