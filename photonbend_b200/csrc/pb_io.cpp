@@ -2,6 +2,7 @@
 //
 // Build (photonbend_b200/build.py):  g++ -O2 -fPIC -shared -I<cuda>/include -Iinclude pb_io.cpp
 //                                        -L<cuda>/lib64 -lnvjpeg -lcudart -o libpbio.so
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -58,7 +59,16 @@ struct Codec {
     nvjpegStatus_t ensure() {
         if (tried) return init_status;
         tried = true;
-        init_status = nvjpegCreateSimple(&handle);
+        // PB_IO_BACKEND: hybrid (Huffman stages on the host), gpu (Huffman stages on the device: large
+        // images), hardware (the JPEG engines, baseline single-scan images); default: the library's choice
+        nvjpegBackend_t backend = NVJPEG_BACKEND_DEFAULT;
+        if (const char* e = std::getenv("PB_IO_BACKEND")) {
+            if (!std::strcmp(e, "hybrid")) backend = NVJPEG_BACKEND_HYBRID;
+            else if (!std::strcmp(e, "gpu")) backend = NVJPEG_BACKEND_GPU_HYBRID;
+            else if (!std::strcmp(e, "hardware")) backend = NVJPEG_BACKEND_HARDWARE;
+        }
+        init_status = backend == NVJPEG_BACKEND_DEFAULT ? nvjpegCreateSimple(&handle)
+                                                         : nvjpegCreateEx(backend, nullptr, nullptr, 0, &handle);
         if (init_status == NVJPEG_STATUS_SUCCESS) init_status = nvjpegJpegStateCreate(handle, &dec_state);
         return init_status;
     }
