@@ -740,7 +740,7 @@ def run_gpu(args):
                 "d2h_bytes_per_step": compressed[2],
                 "api": "photonbend_b200.stream.remap_jpeg_stream: JPEG bytes in, nvJPEG decode + remap (4 frames per "
                        "launch) + nvJPEG encode on the device, JPEG bytes out; smooth synthetic frames, quality 90 in / 75 out",
-                "note": "bounded by the nvJPEG library codec (Huffman stages on the host), not by the remap kernel or PCIe"}
+                "note": "bounded by the nvJPEG library codec (decoupled decoder, Huffman stage on the device, up to 4 decode threads per GPU), not by the remap kernel or PCIe"}
         elif compressed is not None:
             line["e2e_compressed"] = {"unavailable": compressed}
         if sustained:

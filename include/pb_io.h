@@ -40,7 +40,10 @@ int pb_io_jpeg_info(const uint8_t *jpeg, size_t jpeg_bytes, int32_t *width, int3
                     int32_t *components);
 
 /* Decode a host JPEG into dst (device, height x width x 3, RGB interleaved, tightly packed).
- * Grey images are expanded to RGB.  Asynchronous on `stream`. */
+ * Grey images are expanded to RGB.  Enqueued on `stream`; `jpeg` must stay valid until the stream
+ * has run the decode.  Callable from several host threads at once on one device: every thread has
+ * its own decoder state and buffers (nvJPEG's decoupled decoder with the Huffman stage on the
+ * device; PB_IO_DECODER=single|threads selects the others, see pb_io.cpp). */
 int pb_io_jpeg_decode_rgb_u8(const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *dst, int32_t width,
                              int32_t height, void *stream);
 

@@ -17,6 +17,7 @@ Two codecs, as for single files (``utils/image_io.py``):
 
 from __future__ import annotations
 
+import os
 import threading
 import time
 from concurrent.futures import ThreadPoolExecutor
@@ -136,24 +137,29 @@ def _device_worker(device: int, frames: Sequence[int], source, cmap, in_files, o
 
 
 def remap_jpeg_stream(source, coordinate_map: CoordinateMap, jpegs: Sequence[bytes], devices: Optional[Sequence[int]] = None,
-                      batch: int = 4) -> List[bytes]:
+                      batch: int = 4, decode_threads: Optional[int] = None) -> List[bytes]:
     """Compressed stream in memory: JPEG bytes in -> nvJPEG decode on the device -> ONE remap launch
     per ``batch`` frames -> nvJPEG encode on the device -> JPEG bytes out.  Frame k on GPU
-    ``devices[k mod G]``, two host threads per GPU (decode of the next batch overlaps remap + encode
-    of the current one); raw pixels never cross PCIe."""
+    ``devices[k mod G]``; per GPU a producer that decodes batch k + 1 with ``decode_threads`` host
+    threads (each its own decoder state and stream; default: up to 4, at most one per frame of a
+    batch and what the host's cores allow per GPU) while a consumer remaps and encodes batch k; raw
+    pixels never cross PCIe."""
     if not (isinstance(coordinate_map, CoordinateMap) and coordinate_map.is_lazy):
         raise ValueError("remap_jpeg_stream needs the lazy CoordinateMap of get_coordinate_map()")
     torch = engine._torch()
     if devices is None:
         devices = list(range(torch.cuda.device_count()))
     devices = list(devices)[: max(1, len(jpegs))]
+    if decode_threads is None:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        decode_threads = max(1, min(4, batch, cores // len(devices) - 1))
     shape = tuple(source.image.shape)[-3:]  # (H, W, C) of one frame (the image may be a batch)
     out: List[Optional[bytes]] = [None] * len(jpegs)
     errors = []
 
     def run(g):
-        # two host threads per GPU: this one decodes batch k + 1 into the other of two device
-        # buffers (nvJPEG's Huffman stage is host work) while the second one remaps and encodes batch k
+        # per GPU: this thread has batch k + 1 decoded into the other of two device buffers (by
+        # `decode_threads` workers, one frame each) while a second one remaps and encodes batch k
         try:
             device = devices[g]
             frames = list(shard_frames(len(jpegs), g, len(devices)))
@@ -191,17 +197,25 @@ def remap_jpeg_stream(source, coordinate_map: CoordinateMap, jpegs: Sequence[byt
                         for sem in free:
                             sem.release()
 
+                tls = threading.local()
+
+                def decode_one(f, b, i):
+                    if not hasattr(tls, "stream"):
+                        tls.stream = torch.cuda.Stream(device=device)
+                    with torch.cuda.device(device), torch.cuda.stream(tls.stream):
+                        image_io.decode_jpeg_into(jpegs[f], srcs[b][i])  # (synchronises its stream)
+
                 consumer = threading.Thread(target=consume)
                 consumer.start()
                 try:
-                    with torch.cuda.stream(streams[0]):
+                    with ThreadPoolExecutor(max_workers=decode_threads) as pool:
                         for n, chunk in enumerate(chunks):
                             b = n & 1
                             free[b].acquire()
                             if failed:
                                 break
-                            for i, f in enumerate(chunk):
-                                image_io.decode_jpeg_into(jpegs[f], srcs[b][i])  # (synchronises its stream)
+                            for fut in [pool.submit(decode_one, f, b, i) for i, f in enumerate(chunk)]:
+                                fut.result()
                             decoded[b].release()
                 except BaseException as exc:  # noqa: BLE001
                     failed.append(exc)

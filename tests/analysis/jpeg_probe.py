@@ -1,5 +1,5 @@
-"""Decode / encode rates of the nvJPEG bridge (libpbio.so) on one 8K frame, per backend:
-    PB_IO_BACKEND={default,hybrid,gpu,hardware} python tests/analysis/jpeg_probe.py
+"""Decode / encode rates of the nvJPEG bridge (libpbio.so) on one 8K frame, per backend / decoder:
+    PB_IO_BACKEND={default,hybrid,gpu,hardware} PB_IO_DECODER={,gpu,threads} python tests/analysis/jpeg_probe.py [threads]
 Smooth synthetic frame (the one bench.py's e2e_compressed uses), quality 90 in / 75 out."""
 import io
 import os
@@ -24,7 +24,7 @@ def main():
     Image.fromarray(img).save(buf, format="JPEG", quality=90)
     data = buf.getvalue()
     out = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
-    tag = os.environ.get("PB_IO_BACKEND", "default")
+    tag = os.environ.get("PB_IO_BACKEND", "default") + "/" + (os.environ.get("PB_IO_DECODER") or "gpu")
     try:
         image_io.decode_jpeg_into(data, out)
     except Exception as exc:  # noqa: BLE001
@@ -46,8 +46,30 @@ def main():
     torch.cuda.synchronize()
     enc = (time.perf_counter() - t0) / n
     px = h * w / 1e9
-    print(f"{tag:9s} decode {dec * 1e3:7.2f} ms ({px / dec:5.2f} Gpix/s, max |d| vs Pillow {err}), "
+    print(f"{tag:22s} decode {dec * 1e3:7.2f} ms ({px / dec:5.2f} Gpix/s, max |d| vs Pillow {err}), "
           f"encode {enc * 1e3:7.2f} ms ({px / enc:5.2f} Gpix/s), {len(data)} -> {len(enc_bytes)} bytes")
+    n_threads = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    if n_threads > 1:  # several host threads decoding at once into their own tensors, on their own streams
+        import threading
+
+        outs = [torch.empty_like(out) for _ in range(n_threads)]
+
+        def work(k):
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(n):
+                    image_io.decode_jpeg_into(data, outs[k])
+
+        for warm in (True, False):
+            threads = [threading.Thread(target=work, args=(k,)) for k in range(n_threads)]
+            t0 = time.perf_counter()
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        same = all(bool((o == out).all()) for o in outs)
+        print(f"{tag:22s} {n_threads} threads: {n_threads * n * px / dt:5.2f} Gpix/s decoded, outputs equal: {same}")
 
 
 if __name__ == "__main__":

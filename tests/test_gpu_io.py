@@ -37,6 +37,42 @@ def test_device_decode_matches_pillow_within_codec_tolerance():
     assert _psnr(got, want) > 40.0
 
 
+def test_decode_from_several_host_threads_at_once():
+    """Four host threads decode the same file on one GPU, each on its own stream, three times over:
+    every output equals the single-threaded one (a decoder state per thread; the single-state path
+    holds its state until the stream has run the decode)."""
+    import threading
+
+    import torch
+
+    from photonbend_b200.utils import image_io
+
+    with open(os.path.join(GOLDEN, "equidistant.jpg"), "rb") as fh:
+        data = fh.read()
+    want = image_io.decode_jpeg_to_device(data)
+    outs = [torch.zeros_like(want) for _ in range(4)]
+    errors = []
+
+    def work(k):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(3):
+                    outs[k].zero_()
+                    image_io.decode_jpeg_into(data, outs[k])
+        except BaseException as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+    for k in range(4):
+        assert torch.equal(outs[k], want), k
+
+
 def test_device_encode_round_trip():
     """Encode from a CUDA tensor at Pillow's defaults (quality 75, 4:2:0); Pillow decodes the
     bitstream; PSNR against the source > 30 dB on a smooth image, size within 2x of Pillow's own."""
