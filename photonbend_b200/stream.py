@@ -109,31 +109,98 @@ def _host_worker(device: int, frames: Sequence[int], source, cmap, in_files, out
         return pipe.kernel_launches
 
 
-def _device_worker(device: int, frames: Sequence[int], source, cmap, in_files, out_files, batch, shape):
-    """nvJPEG codec: compressed bytes up, decode -> remap -> encode on GPU ``device``, compressed bytes down."""
+def _default_decode_threads(batch: int, n_devices: int) -> int:
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, min(4, batch, cores // max(1, n_devices) - 1))
+
+
+def _compressed_pipeline(device: int, frames: Sequence[int], source, cmap, load, store, batch: int, decode_threads: int,
+                         shape) -> int:
+    """Frames ``frames`` on GPU ``device``, compressed on both sides of PCIe: ``load(k)`` gives the JPEG
+    bytes of frame k, ``store(k, data)`` takes the JPEG bytes of its remap.  A producer (the calling
+    thread) has batch n + 1 decoded into the other of two device buffers by ``decode_threads``
+    workers -- one frame each, every worker its own decoder state and stream -- while a consumer
+    thread remaps batch n (ONE launch) and encodes it.  Returns the number of kernel launches."""
     torch = engine._torch()
-    launches = 0
+    chunks = [frames[c0:c0 + batch] for c0 in range(0, len(frames), batch)]
+    if not chunks:
+        return 0
     with torch.cuda.device(device):
         rays, geom = cmap.rays, source._source_geometry()
-        src = torch.empty((batch,) + tuple(shape), dtype=torch.uint8, device=f"cuda:{device}")
+        srcs = [torch.empty((batch,) + tuple(shape), dtype=torch.uint8, device=f"cuda:{device}") for _ in range(2)]
         dst = torch.empty((batch, rays.out.height, rays.out.output_width, shape[2]), dtype=torch.uint8,
                           device=f"cuda:{device}")
-        for c0 in range(0, len(frames), batch):
-            chunk = frames[c0:c0 + batch]
-            for i, k in enumerate(chunk):
-                with open(in_files[k], "rb") as fh:
-                    image_io.decode_jpeg_into(fh.read(), src[i])
-            n = len(chunk)
-            if n == 1:
-                engine.remap_device(rays, geom, src[0], dst[0])
-            else:
-                engine.remap_device(rays, geom, src[:n], dst[:n])
-            launches += 1
-            for i, k in enumerate(chunk):
-                data = image_io.encode_jpeg_from_device(dst[i])
-                with open(out_files[k], "wb") as fh:
-                    fh.write(data)
-    return launches
+        decoded = [threading.Semaphore(0), threading.Semaphore(0)]  # buffer b holds a decoded batch
+        free = [threading.Semaphore(1), threading.Semaphore(1)]     # buffer b may be overwritten
+        failed: list = []
+        consumer_stream = torch.cuda.Stream(device=device)
+
+        def consume():
+            try:
+                with torch.cuda.device(device), torch.cuda.stream(consumer_stream):
+                    for n, chunk in enumerate(chunks):
+                        b = n & 1
+                        decoded[b].acquire()
+                        if failed:
+                            return
+                        k = len(chunk)
+                        if k == 1:
+                            engine.remap_device(rays, geom, srcs[b][0], dst[0])
+                        else:
+                            engine.remap_device(rays, geom, srcs[b][:k], dst[:k])
+                        torch.cuda.current_stream().synchronize()
+                        free[b].release()  # the remap has read the batch: it may be decoded over
+                        for i, f in enumerate(chunk):
+                            store(f, image_io.encode_jpeg_from_device(dst[i]))
+            except BaseException as exc:  # noqa: BLE001
+                failed.append(exc)
+                for sem in free:
+                    sem.release()
+
+        tls = threading.local()
+
+        def decode_one(f, b, i):
+            if not hasattr(tls, "stream"):
+                tls.stream = torch.cuda.Stream(device=device)
+            with torch.cuda.device(device), torch.cuda.stream(tls.stream):
+                image_io.decode_jpeg_into(load(f), srcs[b][i])  # (synchronises its stream)
+
+        consumer = threading.Thread(target=consume)
+        consumer.start()
+        try:
+            with ThreadPoolExecutor(max_workers=decode_threads) as pool:
+                for n, chunk in enumerate(chunks):
+                    b = n & 1
+                    free[b].acquire()
+                    if failed:
+                        break
+                    for fut in [pool.submit(decode_one, f, b, i) for i, f in enumerate(chunk)]:
+                        fut.result()
+                    decoded[b].release()
+        except BaseException as exc:  # noqa: BLE001
+            failed.append(exc)
+            for sem in decoded:
+                sem.release()
+        consumer.join()
+        if failed:
+            raise failed[0]
+    return len(chunks)
+
+
+def _device_worker(device: int, frames: Sequence[int], source, cmap, in_files, out_files, batch, shape, n_devices=1):
+    """nvJPEG codec on files: compressed bytes up, decode -> remap -> encode on GPU ``device``, compressed bytes down."""
+
+    def load(k):
+        with open(in_files[k], "rb") as fh:
+            return fh.read()
+
+    def store(k, data):
+        with open(out_files[k], "wb") as fh:
+            fh.write(data)
+
+    if batch <= 1:
+        batch = 4  # (frames of a batch are decoded at once; one frame per launch would decode one at a time)
+    return _compressed_pipeline(device, frames, source, cmap, load, store, batch, _default_decode_threads(batch, n_devices), shape)
 
 
 def remap_jpeg_stream(source, coordinate_map: CoordinateMap, jpegs: Sequence[bytes], devices: Optional[Sequence[int]] = None,
@@ -151,79 +218,19 @@ def remap_jpeg_stream(source, coordinate_map: CoordinateMap, jpegs: Sequence[byt
         devices = list(range(torch.cuda.device_count()))
     devices = list(devices)[: max(1, len(jpegs))]
     if decode_threads is None:
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        decode_threads = max(1, min(4, batch, cores // len(devices) - 1))
+        decode_threads = _default_decode_threads(batch, len(devices))
     shape = tuple(source.image.shape)[-3:]  # (H, W, C) of one frame (the image may be a batch)
     out: List[Optional[bytes]] = [None] * len(jpegs)
     errors = []
 
+    def store(k, data):
+        out[k] = data
+
     def run(g):
-        # per GPU: this thread has batch k + 1 decoded into the other of two device buffers (by
-        # `decode_threads` workers, one frame each) while a second one remaps and encodes batch k
         try:
-            device = devices[g]
             frames = list(shard_frames(len(jpegs), g, len(devices)))
-            chunks = [frames[c0:c0 + batch] for c0 in range(0, len(frames), batch)]
-            with torch.cuda.device(device):
-                rays, geom = coordinate_map.rays, source._source_geometry()
-                srcs = [torch.empty((batch,) + shape, dtype=torch.uint8, device=f"cuda:{device}") for _ in range(2)]
-                dst = torch.empty((batch, rays.out.height, rays.out.output_width, shape[2]), dtype=torch.uint8,
-                                  device=f"cuda:{device}")
-                decoded = [threading.Semaphore(0), threading.Semaphore(0)]  # buffer b holds a decoded batch
-                free = [threading.Semaphore(1), threading.Semaphore(1)]     # buffer b may be overwritten
-                failed = []
-
-                streams = [torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)]
-
-                def consume():
-                    try:
-                        with torch.cuda.device(device), torch.cuda.stream(streams[1]):
-                            for n, chunk in enumerate(chunks):
-                                b = n & 1
-                                decoded[b].acquire()
-                                if failed:
-                                    return
-                                k = len(chunk)
-                                if k == 1:
-                                    engine.remap_device(rays, geom, srcs[b][0], dst[0])
-                                else:
-                                    engine.remap_device(rays, geom, srcs[b][:k], dst[:k])
-                                torch.cuda.current_stream().synchronize()
-                                free[b].release()  # the remap has read the batch: it may be decoded over
-                                for i, f in enumerate(chunk):
-                                    out[f] = image_io.encode_jpeg_from_device(dst[i])
-                    except BaseException as exc:  # noqa: BLE001
-                        failed.append(exc)
-                        for sem in free:
-                            sem.release()
-
-                tls = threading.local()
-
-                def decode_one(f, b, i):
-                    if not hasattr(tls, "stream"):
-                        tls.stream = torch.cuda.Stream(device=device)
-                    with torch.cuda.device(device), torch.cuda.stream(tls.stream):
-                        image_io.decode_jpeg_into(jpegs[f], srcs[b][i])  # (synchronises its stream)
-
-                consumer = threading.Thread(target=consume)
-                consumer.start()
-                try:
-                    with ThreadPoolExecutor(max_workers=decode_threads) as pool:
-                        for n, chunk in enumerate(chunks):
-                            b = n & 1
-                            free[b].acquire()
-                            if failed:
-                                break
-                            for fut in [pool.submit(decode_one, f, b, i) for i, f in enumerate(chunk)]:
-                                fut.result()
-                            decoded[b].release()
-                except BaseException as exc:  # noqa: BLE001
-                    failed.append(exc)
-                    for sem in decoded:
-                        sem.release()
-                consumer.join()
-                if failed:
-                    raise failed[0]
+            _compressed_pipeline(devices[g], frames, source, coordinate_map, jpegs.__getitem__, store, batch,
+                                 decode_threads, shape)
         except BaseException as exc:  # noqa: BLE001
             errors.append(exc)
 
@@ -262,7 +269,8 @@ def remap_files(source, coordinate_map: CoordinateMap, in_files: Sequence, out_f
         frames = list(shard_frames(len(in_files), g, len(devices)))
         try:
             if on_device:
-                results[g] = _device_worker(devices[g], frames, source, coordinate_map, in_files, out_files, max(1, batch), shape)
+                results[g] = _device_worker(devices[g], frames, source, coordinate_map, in_files, out_files, max(1, batch), shape,
+                                            len(devices))
             else:
                 results[g] = _host_worker(devices[g], frames, source, coordinate_map, in_files, out_files, depth,
                                           max(1, batch), codec_threads, shape)
