@@ -190,6 +190,15 @@ int pb_map_projection_u8(double *map, int32_t map_height, int32_t map_width, uin
  */
 int pb_debug_fast32_stats(const pb_remap_desc *desc, double stats[6], void *stream);
 
+/*
+ * The FP32-first tier as calibrated for one plan: pb_plan_create measures the largest
+ * |float - double| / (2^-24 * error shape) over the plan's own output pixels (out[1]; -1 when the
+ * plan resolves through tables and needs no tier) and bounds the tier's error with
+ * K = max(1.5, 1.25 * that + 0.25) (out[0]; 0 when the tier is off) instead of the K = 16 that holds for
+ * every geometry.  No reference counterpart.
+ */
+int pb_debug_plan_fast32(const pb_plan *plan, double out[2]);
+
 #ifdef __cplusplus
 }
 #endif

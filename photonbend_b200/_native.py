@@ -41,6 +41,7 @@ EXPORTS = (
     "pb_gather_from_map_u8",
     "pb_map_projection_u8",
     "pb_debug_fast32_stats",
+    "pb_debug_plan_fast32",
 )
 
 
@@ -120,6 +121,8 @@ def load():
     lib.pb_map_projection_u8.argtypes = [vp, i32, i32, vp, vp]
     lib.pb_debug_fast32_stats.restype = ctypes.c_int
     lib.pb_debug_fast32_stats.argtypes = [ctypes.POINTER(RemapDesc), ctypes.POINTER(ctypes.c_double), vp]
+    lib.pb_debug_plan_fast32.restype = ctypes.c_int
+    lib.pb_debug_plan_fast32.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
 

@@ -556,6 +556,33 @@ __global__ void __launch_bounds__(256) fast32_stats_kernel(const __grid_constant
     }
 }
 
+// The calibration half of the above alone (pb_plan_create): largest |float - double| / (2^-24 * shape)
+// of a coordinate over the pixels both evaluations give coordinates for, as float bits.
+template <int OUT_KIND, int SRC_KIND>
+__global__ void __launch_bounds__(256) fast32_ratio_kernel(const __grid_constant__ RemapArgs a,
+                                                           const __grid_constant__ Fast32GeomT<double> gd,
+                                                           unsigned* __restrict__ maxima) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    float r = 0.0f;
+    if (i < a.out.H && j < a.out.W) {
+        const Coords32<float> cf = coords32<float, OUT_KIND, SRC_KIND>(a.out, a.fast.f32, a.src, i, j);
+        if (cf.status != 2) {
+            const Coords32<double> cd = coords32<double, OUT_KIND, SRC_KIND>(a.out, gd, a.src, i, j);
+            const double eps = 5.9604644775390625e-08;
+            if (cf.status == 0 && cd.status == 0)
+                r = fmaxf((float)(fabs((double)cf.vx - cd.vx) / (eps * (double)cf.ex)),
+                          (float)(fabs((double)cf.vy - cd.vy) / (eps * (double)cf.ey)));
+            if (SRC_KIND == PB_KIND_DOUBLE && cd.status != 2 && cf.slot1 == 0 && cd.slot1 == 0)
+                r = fmaxf(r, fmaxf((float)(fabs((double)cf.wx - cd.wx) / (eps * (double)cf.fx_)),
+                                   (float)(fabs((double)cf.wy - cd.wy) / (eps * (double)cf.fy_))));
+            if (!(r >= 0.0f)) r = INFINITY;  // a NaN must not hide behind the maximum
+        }
+    }
+    const unsigned bits = __reduce_max_sync(0xffffffffu, __float_as_uint(r));  // (non-negative floats order like their bits)
+    if ((threadIdx.x & 31) == 0 && bits != 0) atomicMax(maxima, bits);
+}
+
 // get_coordinate_map() + n rotations, materialised.
 template <int OUT_KIND>
 __global__ void __launch_bounds__(256) materialize_map_kernel(const __grid_constant__ OutGeom out,
@@ -753,6 +780,18 @@ static void launch_stats_s(const RemapArgs& a, const Fast32GeomT<double>& gd, un
         case PB_KIND_CAMERA: fast32_stats_kernel<OUT_KIND, PB_KIND_CAMERA><<<grid, block, 0, st>>>(a, gd, maxima, counters); break;
         case PB_KIND_DOUBLE: fast32_stats_kernel<OUT_KIND, PB_KIND_DOUBLE><<<grid, block, 0, st>>>(a, gd, maxima, counters); break;
         default: fast32_stats_kernel<OUT_KIND, PB_KIND_EQUIRECT><<<grid, block, 0, st>>>(a, gd, maxima, counters); break;
+    }
+    PB_COUNT_LAUNCH();
+}
+
+template <int OUT_KIND>
+static void launch_ratio_s(const RemapArgs& a, const Fast32GeomT<double>& gd, unsigned* maxima, cudaStream_t st) {
+    dim3 block(32, 8);
+    dim3 grid((a.out.W + block.x - 1) / block.x, (a.out.H + block.y - 1) / block.y);
+    switch (a.src.kind) {
+        case PB_KIND_CAMERA: fast32_ratio_kernel<OUT_KIND, PB_KIND_CAMERA><<<grid, block, 0, st>>>(a, gd, maxima); break;
+        case PB_KIND_DOUBLE: fast32_ratio_kernel<OUT_KIND, PB_KIND_DOUBLE><<<grid, block, 0, st>>>(a, gd, maxima); break;
+        default: fast32_ratio_kernel<OUT_KIND, PB_KIND_EQUIRECT><<<grid, block, 0, st>>>(a, gd, maxima); break;
     }
     PB_COUNT_LAUNCH();
 }
@@ -1028,6 +1067,8 @@ struct pb_plan {
         CUtensorMap map;
     } dst_cache[kMapSlots];
     unsigned long long tick;
+    double fast32_k;      // K of the FP32-first tier's error bound for this plan (calibrate_fast32; 16 un-calibrated)
+    float fast32_ratio;   // what the calibration measured (-1: not run)
     // launches through one plan are serialised on the host (map caches, side lanes): a plan may be
     // shared by host threads
     std::mutex mu;
@@ -1057,6 +1098,8 @@ static void plan_init(pb_plan& p, const pb_remap_desc& d) {
     std::memcpy(p.rot.m, d.rotations, sizeof(p.rot.m));
     p.fast = derive_fast(d.out, p.out, d.src, p.src, d.n_rotations, d.rotations);
     p.fast.f32 = fast32_to_float(derive_fast32(p.out, p.src, p.fast));
+    p.fast32_k = kFast32K;
+    p.fast32_ratio = -1.0f;
     p.separable = d.out.kind == PB_KIND_EQUIRECT && d.n_rotations == 0 && d.src.kind != PB_KIND_EQUIRECT &&
                   d.channels == 3;
     p.stage_bytes = 24 * 1024;  // un-tuned default (pb_remap_u8 without a plan)
@@ -1720,6 +1763,59 @@ int pb_remap_u8(const pb_remap_desc* desc, const uint8_t* src, int64_t src_frame
     return rc;
 }
 
+// The error bound of the FP32-first tier, K * 2^-24 * shape, holds for every geometry with the K = 16
+// of derive_fast32 (calibrated over the lens pairs of the test matrix: the largest ratio seen is
+// 6.4).  A plan can do better, and rigorously so: float arithmetic is deterministic, so the
+// largest |float - double| / (2^-24 * shape) over THIS plan's own output pixels -- one pass of
+// both evaluations at plan creation, ~1 ms for 8K -- bounds the error of exactly the evaluations
+// its launches will make.  K_plan = 1.25 * that + 0.25 (typical geometries: 2-5, which cuts the
+// pixels that go through the float64 rounds to a quarter); never below 1.5.  A ratio beyond what
+// K = 16 covers (none known) raises K instead, and a wild one switches the tier off.
+static void calibrate_fast32(pb_plan& p, cudaStream_t st) {
+    if (!p.fast.f32.enabled || p.separable) return;  // (separable plans resolve through tables)
+    if (std::getenv("PB_FP32_K")) return;            // calibration experiments set K themselves
+    if (const char* e = std::getenv("PB_FP32_CALIBRATE")) {
+        if (std::atoi(e) == 0) return;
+    }
+    const Fast32GeomT<double> gd = derive_fast32(p.out, p.src, p.fast);
+    RemapArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.out = p.out;
+    a.src = p.src;
+    a.rot = p.rot;
+    a.fast = p.fast;
+    unsigned* dev = nullptr;
+    if (cudaMalloc((void**)&dev, sizeof(unsigned)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;
+    }
+    cudaMemsetAsync(dev, 0, sizeof(unsigned), st);
+    switch (a.out.kind) {
+        case PB_KIND_CAMERA: launch_ratio_s<PB_KIND_CAMERA>(a, gd, dev, st); break;
+        case PB_KIND_DOUBLE: launch_ratio_s<PB_KIND_DOUBLE>(a, gd, dev, st); break;
+        default: launch_ratio_s<PB_KIND_EQUIRECT>(a, gd, dev, st); break;
+    }
+    unsigned bits = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bits, dev, sizeof(bits), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;  // keep the global bound
+    }
+    float ratio;
+    std::memcpy(&ratio, &bits, sizeof(ratio));
+    p.fast32_ratio = ratio;
+    if (!(ratio <= 64.0f)) {  // (NaN / inf too)
+        p.fast.f32.enabled = 0;
+        p.fast32_k = 0.0;
+        return;
+    }
+    p.fast32_k = std::fmax(1.5, 1.25 * (double)ratio + 0.25);
+    p.fast.f32.k_eps = (float)(p.fast32_k * 5.9604644775390625e-08);
+}
+
 int pb_plan_create(const pb_remap_desc* desc, void* stream, pb_plan** plan_out) {
     if (!plan_out) return fail(PB_ERR_INVALID_ARGUMENT, "pb_plan_create: null plan pointer");
     *plan_out = nullptr;
@@ -1748,8 +1844,16 @@ int pb_plan_create(const pb_remap_desc* desc, void* stream, pb_plan** plan_out) 
             return cuda_fail(e, "pb_plan_create tables");
         }
     }
+    calibrate_fast32(*p, (cudaStream_t)stream);
     tune_stage(*p, (cudaStream_t)stream);
     *plan_out = p;
+    return PB_OK;
+}
+
+int pb_debug_plan_fast32(const pb_plan* plan, double out[2]) {
+    if (!plan || !out) return fail(PB_ERR_INVALID_ARGUMENT, "pb_debug_plan_fast32: null pointer");
+    out[0] = plan->fast.f32.enabled ? plan->fast32_k : 0.0;
+    out[1] = plan->fast32_ratio;
     return PB_OK;
 }
 

@@ -709,6 +709,60 @@ def test_fp32_tier_error_bound(torch_cuda):
           f"(bound K = {FP32_TIER_K}), {n_und / n_px:.4f} of the pixels left to the float64 tiers")
 
 
+def test_plan_calibrates_the_fp32_bound(torch_cuda, monkeypatch):
+    """pb_plan_create measures |float - double| / (2^-24 shape) over the plan's own pixels and bounds
+    tier 1 with K = max(1.5, 1.25 ratio + 0.25) instead of the K = 16 that holds for every geometry.
+    For the two rotated BASELINE configurations and three mid-size lens pairs: the plan reports the
+    ratio pb_debug_fast32_stats measures, its K is the formula's, and with THAT K (PB_FP32_K, read
+    by the diagnostics too) tier 1 still decides no pixel differently from the float64 tiers while
+    leaving fewer undecided.  Separable plans (tables) do not calibrate."""
+    import ctypes
+
+    import torch
+
+    from photonbend_b200 import _native, engine, workloads
+
+    lib = _native.load()
+    outs, srcs = _mid_size_geometries()
+    geoms = [(workloads.WORKLOADS[n]["out"], workloads.WORKLOADS[n]["rotations"], workloads.WORKLOADS[n]["src"])
+             for n in ("cfg2", "cfg3")]
+    geoms += [(outs[k % len(outs)], ((0.3, -0.2, 1.0),), srcs[(2 * k + 1) % len(srcs)]) for k in range(3)]
+    for og, rots, sg in geoms:
+        monkeypatch.delenv("PB_FP32_K", raising=False)
+        try:
+            base = fp32_tier_stats(og, rots, sg)
+        except ValueError:
+            continue
+        cmap = helpers.product_map(og, rots)
+        src = helpers.product_image(sg, np.zeros((sg["height"], sg["width"], 3), np.uint8))
+        desc = engine._remap_desc(cmap.rays, src._source_geometry(), 3)
+        plan = engine._plans.get(lib, desc, torch.cuda.current_device(), torch)
+        got = (ctypes.c_double * 2)()
+        _native.check(lib.pb_debug_plan_fast32(plan, got))
+        k_plan, ratio = float(got[0]), float(got[1])
+        if sg["kind"] == "double" and not rots:
+            continue
+        want_ratio = max(base["max_ratio_x"], base["max_ratio_y"])
+        assert abs(ratio - want_ratio) <= 1e-3 * max(1.0, want_ratio), (og, sg, ratio, want_ratio)
+        assert k_plan == pytest.approx(max(1.5, 1.25 * ratio + 0.25), rel=1e-6) and k_plan <= 16.0, (og, sg, k_plan)
+        monkeypatch.setenv("PB_FP32_K", repr(k_plan))
+        tight = fp32_tier_stats(og, rots, sg)
+        assert tight["wrong"] == 0 and tight["status_mismatch"] == 0, (og, sg, tight)
+        assert tight["undecided"] <= base["undecided"], (og, sg, tight["undecided"], base["undecided"])
+        print(f"{og['kind']} <- {sg['kind']}: ratio {ratio:.2f}, K {k_plan:.2f}, undecided {base['undecided'] / base['pixels']:.4f} "
+              f"-> {tight['undecided'] / tight['pixels']:.4f}")
+    monkeypatch.delenv("PB_FP32_K", raising=False)
+    # an un-rotated panorama output through a camera source resolves through tables: nothing to calibrate
+    og, sg = {"kind": "equirect", "height": 128, "width": 256}, srcs[0]
+    if sg["kind"] == "camera":
+        src = helpers.product_image(sg, np.zeros((sg["height"], sg["width"], 3), np.uint8))
+        desc = engine._remap_desc(helpers.product_map(og, ()).rays, src._source_geometry(), 3)
+        plan = engine._plans.get(lib, desc, torch.cuda.current_device(), torch)
+        got = (ctypes.c_double * 2)()
+        _native.check(lib.pb_debug_plan_fast32(plan, got))
+        assert float(got[1]) == -1.0
+
+
 def test_map_projection_on_device(torch_cuda, golden_small):
     """core.map_projection (pb_map_projection_u8, reference projection.py:550-599): bit-identical to
     the live reference's outputs on the reference's own maps (ndarray argument: uploaded, invalid
