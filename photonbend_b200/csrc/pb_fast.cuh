@@ -45,6 +45,7 @@ struct Fast32GeomT {
     T x0, y0;
     T inv_f, quarter_inv_f2;  // 1 / f, 0.25 / f^2
     T r2_valid, r2_invalid, r2_domain;
+    T r2_nan;  // r^2 >= r2_nan: beyond the lens inverse's domain, the reference's ray is NaN (not flagged invalid)
     // output side, equirect: lon = col * lon_step + lon0, lat = row * lat_step
     T lon0, lon_step, lat_step;
     // source side
@@ -68,6 +69,7 @@ inline Fast32Geom fast32_to_float(const Fast32GeomT<double>& d) {
     f.r2_valid = (float)d.r2_valid;
     f.r2_invalid = (float)d.r2_invalid;
     f.r2_domain = (float)d.r2_domain;
+    f.r2_nan = (float)d.r2_nan;
     f.lon0 = (float)d.lon0;
     f.lon_step = (float)d.lon_step;
     f.lat_step = (float)d.lat_step;

@@ -117,8 +117,10 @@ __device__ __forceinline__ int out_vector32(const OutGeom& g, const Fast32GeomT<
     if (right) x = -x;
     const T y = fg.y0 - (T)i;
     const T r2 = O::fma(x, x, y * y);
+    // outside the fov (the reference flags the ray invalid: black) -- but only where the lens inverse is
+    // still defined: beyond its domain the reference's latitude is NaN, which no comparison flags
+    if (!(r2 < fg.r2_valid)) return (r2 > fg.r2_invalid && r2 < fg.r2_nan) ? 1 : 2;
     if (!(r2 < fg.r2_domain)) return 2;
-    if (!(r2 < fg.r2_valid)) return (r2 > fg.r2_invalid) ? 1 : 2;
     const T inv_f = fg.inv_f;
     const int lens = g.lens;  // (uniform: an if-chain costs two instructions per test, a jump table seven)
     T k;  // sin(lat) / r

@@ -291,7 +291,7 @@ static Fast32GeomT<double> derive_fast32(const OutGeom& o, const SrcGeom& s, con
     if (o.H > (1 << 20) || o.W > (1 << 20) || s.H > (1 << 20) || s.W > (1 << 20)) d.enabled = 0;
     d.has_rot = g.has_rot;
     std::memcpy(d.rot, g.rot, sizeof(d.rot));
-    d.r2_valid = d.r2_invalid = d.r2_domain = inf;
+    d.r2_valid = d.r2_invalid = d.r2_domain = d.r2_nan = inf;
     if (o.kind == PB_KIND_EQUIRECT) {
         d.lon0 = o.x_start;
         d.lon_step = o.x_step;
@@ -327,6 +327,13 @@ static Fast32GeomT<double> derive_fast32(const OutGeom& o, const SrcGeom& s, con
             case PB_LENS_ORTHOGRAPHIC: d.r2_domain = f * f * 0.94; break;          // lat < 76 deg
             case PB_LENS_THOBY: d.r2_domain = 1.47 * 1.47 * f * f * 0.94; break;
             case PB_LENS_EQUIDISTANT: d.r2_domain = (kPi * 0.999 * f) * (kPi * 0.999 * f); break;
+            default: break;
+        }
+        // where asin() of the lens inverse leaves its domain (a NaN ray in the reference), with a guard
+        switch (o.lens) {
+            case PB_LENS_EQUISOLID: d.r2_nan = 4.0 * f * f * (1.0 - 1e-5); break;
+            case PB_LENS_ORTHOGRAPHIC: d.r2_nan = f * f * (1.0 - 1e-5); break;
+            case PB_LENS_THOBY: d.r2_nan = 1.47 * 1.47 * f * f * (1.0 - 1e-5); break;
             default: break;
         }
     }
