@@ -3,7 +3,11 @@
 // together.  This is the ceiling of bench.py's `e2e` figure (every frame crosses PCIe twice); the
 // remap kernel is not involved.
 //
-//   nvcc -O2 -o host_copy_ceiling host_copy_ceiling.cu && ./host_copy_ceiling [n_gpus] [seconds]
+//   nvcc -O2 -o host_copy_ceiling host_copy_ceiling.cu && ./host_copy_ceiling [n_gpus] [seconds] [h2d_fraction] [rects]
+//
+// h2d_fraction < 1: every upload carries only that share of a frame (what an upload restricted to
+// the source pixels a plan reads would move); rects > 0: as that many 2-D copies (row bands of a
+// narrower rectangle) instead of one contiguous block.
 //
 // One JSON line per (n_gpus, mode): aggregate GB/s each way and the Gpix/s of an 8K RGB stream that
 // bandwidth carries (one frame in + one frame out per 29.49 Mpix).
@@ -25,6 +29,8 @@
 
 constexpr size_t kFrame = 3840ull * 7680ull * 3ull;
 constexpr int kDepth = 3;  // frames in flight per GPU and direction (the pipeline's depth)
+static double g_h2d_fraction = 1.0;
+static int g_rects = 0;
 
 struct Gpu {
     cudaStream_t up[kDepth], down[kDepth];
@@ -48,7 +54,17 @@ static double run(std::vector<Gpu>& gpus, bool h2d, bool d2h, double seconds, lo
             for (int g = 0; g < n; ++g) {
                 CK(cudaSetDevice(g));
                 for (int k = 0; k < kDepth; ++k) {
-                    if (h2d) CK(cudaMemcpyAsync(gpus[g].d_in[k], gpus[g].h_in[k], kFrame, cudaMemcpyHostToDevice, gpus[g].up[k]));
+                    if (h2d && g_rects <= 0) {
+                        const size_t bytes = (size_t)((double)kFrame * g_h2d_fraction) & ~(size_t)255;
+                        CK(cudaMemcpyAsync(gpus[g].d_in[k], gpus[g].h_in[k], bytes, cudaMemcpyHostToDevice, gpus[g].up[k]));
+                    } else if (h2d) {
+                        const size_t pitch = 7680ull * 3ull, rows = 3840 / g_rects;
+                        const size_t width = (size_t)((double)pitch * g_h2d_fraction) & ~(size_t)15;
+                        for (int r = 0; r < g_rects; ++r)
+                            CK(cudaMemcpy2DAsync(gpus[g].d_in[k] + r * rows * pitch + 16 * r, pitch,
+                                                 gpus[g].h_in[k] + r * rows * pitch + 16 * r, pitch, width, rows,
+                                                 cudaMemcpyHostToDevice, gpus[g].up[k]));
+                    }
                     if (d2h) CK(cudaMemcpyAsync(gpus[g].h_out[k], gpus[g].d_out[k], kFrame, cudaMemcpyDeviceToHost, gpus[g].down[k]));
                 }
             }
@@ -69,6 +85,8 @@ int main(int argc, char** argv) {
     int n = argc > 1 ? std::atoi(argv[1]) : n_dev;
     if (n > n_dev) n = n_dev;
     const double seconds = argc > 2 ? std::atof(argv[2]) : 2.0;
+    if (argc > 3) g_h2d_fraction = std::atof(argv[3]);
+    if (argc > 4) g_rects = std::atoi(argv[4]);
     std::vector<Gpu> gpus(n);
     for (int g = 0; g < n; ++g) {
         CK(cudaSetDevice(g));
@@ -91,9 +109,9 @@ int main(int argc, char** argv) {
         const double gbs = (double)frames * (double)kFrame / dt / 1e9;
         // an e2e stream needs one frame up and one frame down per output frame
         const double gpix = (double)frames * 3840.0 * 7680.0 / dt / 1e9;
-        std::printf("{\"n_gpus\": %d, \"mode\": \"%s\", \"GBps_each_way\": %.2f, \"frames_per_s_each_way\": %.1f, "
+        std::printf("{\"n_gpus\": %d, \"h2d_fraction\": %.2f, \"rects\": %d, \"mode\": \"%s\", \"GBps_each_way\": %.2f, \"frames_per_s_each_way\": %.1f, "
                     "\"gpix_per_s_if_stream\": %.2f, \"seconds\": %.2f}\n",
-                    n, names[mode], gbs, frames / dt, mode == 2 ? gpix : 0.0, dt);
+                    n, g_h2d_fraction, g_rects, names[mode], gbs, frames / dt, mode == 2 ? gpix : 0.0, dt);
         std::fflush(stdout);
     }
     return 0;
