@@ -40,6 +40,17 @@ struct Gpu {
     unsigned char* d_out[kDepth];
 };
 
+// rects = -1: the upload as a KERNEL that reads the pinned host frame in place (mapped memory),
+// row by row, only the first h2d_fraction of every row -- spans of the rows instead of a block
+__global__ void __launch_bounds__(256) upload_rows_kernel(const uint4* __restrict__ host, uint4* __restrict__ dev, int pitch16,
+                                                          int width16, int rows) {
+    const long long n = (long long)width16 * rows;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / width16), c = (int)(i - (long long)r * width16);
+        dev[(long long)r * pitch16 + c] = host[(long long)r * pitch16 + c];
+    }
+}
+
 static double run(std::vector<Gpu>& gpus, bool h2d, bool d2h, double seconds, long long* frames_each_way) {
     const int n = (int)gpus.size();
     long long copies = 0;
@@ -54,7 +65,12 @@ static double run(std::vector<Gpu>& gpus, bool h2d, bool d2h, double seconds, lo
             for (int g = 0; g < n; ++g) {
                 CK(cudaSetDevice(g));
                 for (int k = 0; k < kDepth; ++k) {
-                    if (h2d && g_rects <= 0) {
+                    if (h2d && g_rects < 0) {
+                        const int pitch16 = 7680 * 3 / 16, width16 = (int)(pitch16 * g_h2d_fraction);
+                        upload_rows_kernel<<<-g_rects * 148, 256, 0, gpus[g].up[k]>>>(
+                            reinterpret_cast<const uint4*>(gpus[g].h_in[k]), reinterpret_cast<uint4*>(gpus[g].d_in[k]), pitch16,
+                            width16, 3840);
+                    } else if (h2d && g_rects == 0) {
                         const size_t bytes = (size_t)((double)kFrame * g_h2d_fraction) & ~(size_t)255;
                         CK(cudaMemcpyAsync(gpus[g].d_in[k], gpus[g].h_in[k], bytes, cudaMemcpyHostToDevice, gpus[g].up[k]));
                     } else if (h2d) {
