@@ -33,6 +33,10 @@ enum { PB_IO_OK = 0, PB_IO_ERR_INVALID_ARGUMENT = 1, PB_IO_ERR_UNSUPPORTED = 2, 
 enum { PB_IO_CSS_444 = 0, PB_IO_CSS_422 = 1, PB_IO_CSS_420 = 2 };
 
 int pb_io_version(void);
+
+/* Diagnostics: how many decodes of this process took nvjpegDecode on the device's single decoder
+ * state (serialised; PB_IO_DECODER=single, or an image the decoupled decoder refused). */
+long long pb_io_single_state_decodes(void);
 const char *pb_io_last_error(void);
 
 /* Size and component count (1 = grey, 3 = colour) of a JPEG held in host memory. */

@@ -2,6 +2,7 @@
 //
 // Build (photonbend_b200/build.py):  g++ -O2 -fPIC -shared -I<cuda>/include -Iinclude pb_io.cpp
 //                                        -L<cuda>/lib64 -lnvjpeg -lcudart -o libpbio.so
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -16,6 +17,7 @@
 namespace {
 
 thread_local std::string g_error;
+std::atomic<long long> g_single_state_decodes{0};  // decodes that went through nvjpegDecode on the device's one state
 
 int fail(int code, const std::string& msg) {
     g_error = msg;
@@ -146,6 +148,8 @@ extern "C" {
 
 int pb_io_version(void) { return 1; }
 
+long long pb_io_single_state_decodes(void) { return g_single_state_decodes.load(std::memory_order_relaxed); }
+
 const char* pb_io_last_error(void) { return g_error.c_str(); }
 
 int pb_io_jpeg_info(const uint8_t* jpeg, size_t jpeg_bytes, int32_t* width, int32_t* height, int32_t* components) {
@@ -220,6 +224,7 @@ int pb_io_jpeg_decode_rgb_u8(const uint8_t* jpeg, size_t jpeg_bytes, uint8_t* ds
         }
         guard.lock();  // (progressive, 4-component ... images: the single-state decoder takes them)
     }
+    g_single_state_decodes.fetch_add(1, std::memory_order_relaxed);
     s = nvjpegDecode(c.handle, c.dec_state, jpeg, jpeg_bytes, NVJPEG_OUTPUT_RGBI, &img, (cudaStream_t)stream);
     if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_decode_rgb_u8");
     // the state's device buffers are in use until the stream has run the decode: another host thread

@@ -111,7 +111,7 @@ def _host_worker(device: int, frames: Sequence[int], source, cmap, in_files, out
 
 def _default_decode_threads(batch: int, n_devices: int) -> int:
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    return max(1, min(4, batch, cores // max(1, n_devices) - 1))
+    return max(1, min(8, batch, cores // max(1, n_devices) - 1))
 
 
 def _compressed_pipeline(device: int, frames: Sequence[int], source, cmap, load, store, batch: int, decode_threads: int,
@@ -199,16 +199,16 @@ def _device_worker(device: int, frames: Sequence[int], source, cmap, in_files, o
             fh.write(data)
 
     if batch <= 1:
-        batch = 4  # (frames of a batch are decoded at once; one frame per launch would decode one at a time)
+        batch = 8  # (frames of a batch are decoded at once; one frame per launch would decode one at a time)
     return _compressed_pipeline(device, frames, source, cmap, load, store, batch, _default_decode_threads(batch, n_devices), shape)
 
 
 def remap_jpeg_stream(source, coordinate_map: CoordinateMap, jpegs: Sequence[bytes], devices: Optional[Sequence[int]] = None,
-                      batch: int = 4, decode_threads: Optional[int] = None) -> List[bytes]:
+                      batch: int = 8, decode_threads: Optional[int] = None) -> List[bytes]:
     """Compressed stream in memory: JPEG bytes in -> nvJPEG decode on the device -> ONE remap launch
     per ``batch`` frames -> nvJPEG encode on the device -> JPEG bytes out.  Frame k on GPU
     ``devices[k mod G]``; per GPU a producer that decodes batch k + 1 with ``decode_threads`` host
-    threads (each its own decoder state and stream; default: up to 4, at most one per frame of a
+    threads (each its own decoder state and stream; default: up to 8, at most one per frame of a
     batch and what the host's cores allow per GPU) while a consumer remaps and encodes batch k; raw
     pixels never cross PCIe."""
     if not (isinstance(coordinate_map, CoordinateMap) and coordinate_map.is_lazy):

@@ -32,6 +32,7 @@ LIB_PATH = os.path.join(PKG, "libpbio.so")
 # every symbol include/pb_io.h declares
 EXPORTS = (
     "pb_io_version",
+    "pb_io_single_state_decodes",
     "pb_io_last_error",
     "pb_io_jpeg_info",
     "pb_io_jpeg_decode_rgb_u8",
@@ -68,6 +69,8 @@ def load_codec():
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
     lib.pb_io_version.restype = ctypes.c_int
     lib.pb_io_version.argtypes = []
+    lib.pb_io_single_state_decodes.restype = ctypes.c_longlong
+    lib.pb_io_single_state_decodes.argtypes = []
     lib.pb_io_last_error.restype = ctypes.c_char_p
     lib.pb_io_last_error.argtypes = []
     lib.pb_io_jpeg_info.restype = ctypes.c_int
