@@ -44,8 +44,8 @@ int pb_io_jpeg_info(const uint8_t *jpeg, size_t jpeg_bytes, int32_t *width, int3
                     int32_t *components);
 
 /* Decode a host JPEG into dst (device, height x width x 3, RGB interleaved, tightly packed).
- * Grey images are expanded to RGB.  Enqueued on `stream`; `jpeg` must stay valid until the stream
- * has run the decode.  Callable from several host threads at once on one device: every thread has
+ * Grey images are expanded to RGB.  Runs on `stream` and returns when the image is there (the
+ * calling thread sleeps meanwhile: several decode threads per GPU do not cost a core each).  Callable from several host threads at once on one device: every thread has
  * its own decoder state and buffers (nvJPEG's decoupled decoder with the Huffman stage on the
  * device; PB_IO_DECODER=single|threads selects the others, see pb_io.cpp). */
 int pb_io_jpeg_decode_rgb_u8(const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *dst, int32_t width,

@@ -114,7 +114,10 @@ struct ThreadDecoder {
         if (status == NVJPEG_STATUS_SUCCESS) status = nvjpegDecodeParamsSetOutputFormat(params, NVJPEG_OUTPUT_RGBI);
         if (status == NVJPEG_STATUS_SUCCESS) status = nvjpegStateAttachPinnedBuffer(state, pinned);
         if (status == NVJPEG_STATUS_SUCCESS) status = nvjpegStateAttachDeviceBuffer(state, device);
-        if (status == NVJPEG_STATUS_SUCCESS && cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess)
+        // (blocking: a thread that waits for its decode sleeps instead of spinning on a core the other
+        // decode threads -- and the other ranks of a multi-GPU box -- need)
+        if (status == NVJPEG_STATUS_SUCCESS &&
+            cudaEventCreateWithFlags(&done, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
             status = NVJPEG_STATUS_ALLOCATOR_FAILURE;
         return status;
     }
@@ -219,7 +222,10 @@ int pb_io_jpeg_decode_rgb_u8(const uint8_t* jpeg, size_t jpeg_bytes, uint8_t* ds
             if (s == NVJPEG_STATUS_SUCCESS) s = nvjpegDecodeJpegTransferToDevice(c.handle, d.decoder, d.state, d.stream, st);
             if (s == NVJPEG_STATUS_SUCCESS) s = nvjpegDecodeJpegDevice(c.handle, d.decoder, d.state, &img, st);
             if (s != NVJPEG_STATUS_SUCCESS) return codec_fail(s, "pb_io_jpeg_decode_rgb_u8 (decoupled decoder)");
-            cudaEventRecord(d.done, st);
+            // wait here, asleep, for the device stages: the caller's own synchronize then returns at once
+            static const bool spin = std::getenv("PB_IO_SPIN") && std::atoi(std::getenv("PB_IO_SPIN")) != 0;  // A/B runs
+            if (cudaEventRecord(d.done, st) != cudaSuccess || (!spin && cudaEventSynchronize(d.done) != cudaSuccess))
+                return fail(PB_IO_ERR_CUDA, "pb_io_jpeg_decode_rgb_u8: waiting for the decode");
             return PB_IO_OK;
         }
         guard.lock();  // (progressive, 4-component ... images: the single-state decoder takes them)

@@ -111,7 +111,8 @@ def _host_worker(device: int, frames: Sequence[int], source, cmap, in_files, out
 
 def _default_decode_threads(batch: int, n_devices: int) -> int:
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    return max(1, min(8, batch, cores // max(1, n_devices) - 1))
+    # (per GPU: the producer, the consumer and the decode threads; half of what is left of this GPU's share of the cores)
+    return max(1, min(8, batch, (cores // max(1, n_devices) - 2) // 2 + 1))
 
 
 def _compressed_pipeline(device: int, frames: Sequence[int], source, cmap, load, store, batch: int, decode_threads: int,
